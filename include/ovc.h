@@ -1,0 +1,137 @@
+/*
+ * ovc.h -- C ABI of libovc_b200.so: the tone-colour-converter hot path of OpenVoice
+ * (ToneColorConverter.convert -> SynthesizerTrn.voice_conversion) as hand-written
+ * sm_100a CUDA kernels.
+ *
+ * The reference has no FFI / plugin interface (it is pure Python).  The
+ * boundary this library replaces is the Python seam
+ *
+ *     model.voice_conversion(y, y_lengths, sid_src, sid_tgt, tau)
+ *         -> (o_hat[B,1,256T], y_mask[B,1,T], (z, z_p, z_hat))      openvoice/models.py:492-499
+ *
+ * called from openvoice/api.py:154, plus checkpoint loading (openvoice/api.py:35-39) and model
+ * construction from the JSON hparams (openvoice/api.py:21-28).  Entry points take plain
+ * pointers and sizes only -- no torch types.  All functions return 0 on success and a negative
+ * status otherwise; ovc_last_error() gives the message.  Nothing here ever falls back to a CPU
+ * path: without a CUDA device every compute entry point fails.
+ */
+#ifndef OVC_B200_H
+#define OVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define OVC_API __attribute__((visibility("default")))
+#else
+#define OVC_API
+#endif
+
+enum {
+  OVC_OK = 0,
+  OVC_ERR_INVALID = -1,     /* bad argument / unsupported hyper-parameter               */
+  OVC_ERR_CUDA = -2,        /* CUDA runtime error (message has cudaGetErrorString)      */
+  OVC_ERR_STATE = -3,       /* call order violated (e.g. convert before finalize)       */
+  OVC_ERR_MISSING = -4,     /* a checkpoint tensor needed by the hot path is missing    */
+  OVC_ERR_NOMEM = -5
+};
+
+typedef struct ovc_ctx ovc_ctx;
+
+/* Mirrors the `model` / `data` sections of the converter config.json that
+ * OpenVoiceBaseClass.__init__ splats into SynthesizerTrn (openvoice/api.py:21-28,
+ * openvoice/models.py:404-465).  The kernels are specialised for the released family
+ * (SURVEY.md appendix A.1); anything else is refused by ovc_create with OVC_ERR_INVALID. */
+typedef struct ovc_hparams {
+  int32_t spec_channels;            /* filter_length/2+1 = 513          api.py:25            */
+  int32_t inter_channels;           /* 192                              models.py:408        */
+  int32_t hidden_channels;          /* 192                              models.py:409        */
+  int32_t gin_channels;             /* 256                              models.py:422        */
+  int32_t resblock;                 /* 1 (ResBlock1)                    models.py:242        */
+  int32_t n_resblock_kernels;       /* 3                                                     */
+  int32_t resblock_kernel_sizes[4]; /* 3,7,11                           models.py:261-264    */
+  int32_t resblock_dilations[4][3]; /* {1,3,5} each                                          */
+  int32_t n_upsamples;              /* 4                                                     */
+  int32_t upsample_rates[4];        /* 8,8,2,2                          models.py:245-256    */
+  int32_t upsample_kernel_sizes[4]; /* 16,16,4,4                                             */
+  int32_t upsample_initial_channel; /* 512                                                   */
+  int32_t zero_g;                   /* V2: g zeroed for enc_q and dec   models.py:423,495,498*/
+  int32_t hop_length;               /* 256 (= product of upsample_rates)                     */
+} ovc_hparams;
+
+/* ABI version of the loaded library (== OVC_ABI_VERSION it was built with). */
+OVC_API int ovc_abi_version(void);
+
+/* Last error message of this thread ("" if none). Never NULL. */
+OVC_API const char* ovc_last_error(void);
+
+/* Build a converter context on CUDA device `device` (replaces SynthesizerTrn construction,
+ * openvoice/api.py:23-30).  Fails with OVC_ERR_CUDA when no usable sm_100 device exists. */
+OVC_API int ovc_create(const ovc_hparams* hp, int device, ovc_ctx** out);
+OVC_API void ovc_destroy(ovc_ctx* ctx);
+
+/* Feed one checkpoint tensor under its reference state-dict key, fp32, C-contiguous, host
+ * memory (replaces load_state_dict(strict=False), openvoice/api.py:35-39; key schema in
+ * SURVEY.md appendix A.2, weight-norm stored un-folded as weight_g / weight_v).  Keys that the
+ * hot path does not use (ref_enc.*, enc_p.*, ...) are accepted and ignored (returns 1). */
+OVC_API int ovc_load_tensor(ovc_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim);
+
+/* Fold weight-norm (g*v/||v||, per dim-0 slice), absorb the channel Flips of the flow into the
+ * coupling weights, repack every conv for the kernels and upload.  OVC_ERR_MISSING names the
+ * first missing key. */
+OVC_API int ovc_finalize_weights(ovc_ctx* ctx);
+
+/* Number of floats of device workspace a call with (B, Tmax) needs (informational; the arena
+ * grows on demand and is reused, so steady-state calls do not allocate). */
+OVC_API size_t ovc_workspace_floats(const ovc_ctx* ctx, int B, int Tmax);
+
+/* The hot path.  All pointers are DEVICE pointers on the context's device; the call only
+ * enqueues work on `stream` (a cudaStream_t; NULL = default stream) and returns.
+ *
+ *   spec     [B, spec_channels, Tmax]  linear magnitude spectrogram            (api.py:150-152)
+ *   lengths  [B] int64, valid frames per item (1 <= len <= Tmax)               (api.py:153)
+ *   g_src    [B, gin] source tone-colour embedding (sid_src, [B,gin,1])        (models.py:493)
+ *   g_tgt    [B, gin] target tone-colour embedding (sid_tgt)
+ *   noise    [B, inter, Tmax] N(0,1) draws standing in for randn_like at models.py:220,
+ *            or NULL: the kernel then draws Philox4x32-10 normals from `seed`
+ *   tau      scales the noise term only                                        (models.py:220)
+ *   ragged   0: reference batch semantics -- the (unmasked) generator runs over all Tmax frames
+ *               of every item exactly as SynthesizerTrn.voice_conversion does on a padded batch
+ *            1: every item is converted at its own exact length, i.e. what
+ *               ToneColorConverter.convert (batch 1, api.py:148-154) produces per utterance
+ *   o_hat    [B, hop*Tmax] waveform out (zero past hop*len when ragged)        (models.py:498)
+ *   z, z_p, z_hat  [B, inter, Tmax] latents, masked like the reference; each may be NULL
+ */
+OVC_API int ovc_voice_conversion(ovc_ctx* ctx, const float* spec, const int64_t* lengths,
+                         const float* g_src, const float* g_tgt, const float* noise,
+                         uint64_t seed, float tau, int B, int Tmax, int ragged,
+                         float* o_hat, float* z, float* z_p, float* z_hat, void* stream);
+
+/* Number of kernels the last ovc_voice_conversion call on this context launched. */
+OVC_API int ovc_last_launch_count(const ovc_ctx* ctx);
+
+/* Per-call timing hook for bench.py's roofline: when enabled, the dominant kernel family
+ * (generator ResBlock convolutions) is bracketed with CUDA events on `stream`.  After the
+ * stream has been synchronised, ovc_profile_read returns the accumulated milliseconds, the
+ * number of launches, their algorithmic FLOPs and their algorithmic (layer-granular) bytes
+ * since the last reset. */
+OVC_API int ovc_profile_enable(ovc_ctx* ctx, int enable);
+OVC_API int ovc_profile_read(ovc_ctx* ctx, double* ms, int64_t* launches, double* flops, double* bytes);
+
+/* Debug taps (tests only): when enabled, named intermediate tensors of the next call are
+ * copied aside; ovc_debug_fetch copies one to host memory.  Names: "enc.pre", "enc.wn",
+ * "dec.pre", "dec.ups0".."dec.ups3", "dec.stage0".."dec.stage3", "cond". */
+OVC_API int ovc_debug_enable(ovc_ctx* ctx, int enable);
+OVC_API int ovc_debug_fetch(ovc_ctx* ctx, const char* name, float* host_out, size_t max_floats,
+                    int64_t* shape4 /* B, C, T, pitch */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVC_B200_H */

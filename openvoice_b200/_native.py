@@ -1,0 +1,224 @@
+"""ctypes binding of libovc_b200.so (C ABI: include/ovc.h).
+
+PyTorch is used for device memory and streams only; every tensor crosses the boundary as a raw
+device pointer.  If the library is missing or no sm_100 GPU is present this module raises --
+there is no fallback path of any kind.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, Optional, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libovc_b200.so")
+
+ABI_VERSION = 1
+EXPORTS = (
+    "ovc_abi_version", "ovc_last_error", "ovc_create", "ovc_destroy", "ovc_load_tensor",
+    "ovc_finalize_weights", "ovc_workspace_floats", "ovc_voice_conversion", "ovc_last_launch_count",
+    "ovc_profile_enable", "ovc_profile_read", "ovc_debug_enable", "ovc_debug_fetch",
+)
+
+
+class OvcHParams(C.Structure):
+    """struct ovc_hparams of include/ovc.h."""
+    _fields_ = [
+        ("spec_channels", C.c_int32), ("inter_channels", C.c_int32), ("hidden_channels", C.c_int32),
+        ("gin_channels", C.c_int32), ("resblock", C.c_int32), ("n_resblock_kernels", C.c_int32),
+        ("resblock_kernel_sizes", C.c_int32 * 4), ("resblock_dilations", (C.c_int32 * 3) * 4),
+        ("n_upsamples", C.c_int32), ("upsample_rates", C.c_int32 * 4),
+        ("upsample_kernel_sizes", C.c_int32 * 4), ("upsample_initial_channel", C.c_int32),
+        ("zero_g", C.c_int32), ("hop_length", C.c_int32),
+    ]
+
+
+class OvcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the CUDA library (once).  Raises OvcError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or os.environ.get("OVC_B200_LIB", LIB_PATH)
+    if not os.path.exists(path):
+        raise OvcError(
+            f"{path} not found: build the sm_100a extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()' or make -C openvoice_b200/csrc). "
+            "openvoice_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(path)
+    lib.ovc_abi_version.restype = C.c_int
+    lib.ovc_last_error.restype = C.c_char_p
+    lib.ovc_create.argtypes = [C.POINTER(OvcHParams), C.c_int, C.POINTER(C.c_void_p)]
+    lib.ovc_destroy.argtypes = [C.c_void_p]
+    lib.ovc_destroy.restype = None
+    lib.ovc_load_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+    lib.ovc_finalize_weights.argtypes = [C.c_void_p]
+    lib.ovc_workspace_floats.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.ovc_workspace_floats.restype = C.c_size_t
+    lib.ovc_voice_conversion.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float,
+        C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ovc_last_launch_count.argtypes = [C.c_void_p]
+    lib.ovc_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.ovc_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ovc_debug_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.ovc_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
+    if lib.ovc_abi_version() != ABI_VERSION:
+        raise OvcError(f"ABI mismatch: library {lib.ovc_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc: int, what: str):
+    if rc < 0:
+        msg = lib.ovc_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise OvcError(f"{what}: {msg} (status {rc})")
+
+
+def hparams_struct(hps) -> OvcHParams:
+    """Build struct ovc_hparams from the reference-style config tree (utils.HParams or dict)."""
+    def get(obj, k, default=None):
+        if isinstance(obj, dict):
+            return obj.get(k, default)
+        return getattr(obj, k, default)
+
+    model, data = get(hps, "model"), get(hps, "data")
+    s = OvcHParams()
+    s.spec_channels = int(get(data, "filter_length")) // 2 + 1
+    s.inter_channels = int(get(model, "inter_channels"))
+    s.hidden_channels = int(get(model, "hidden_channels"))
+    s.gin_channels = int(get(model, "gin_channels", 256))
+    rb = str(get(model, "resblock"))
+    s.resblock = 1 if rb == "1" else 2
+    ks = list(get(model, "resblock_kernel_sizes"))
+    ds = [list(d) for d in get(model, "resblock_dilation_sizes")]
+    if len(ks) > 4 or any(len(d) != 3 for d in ds) or len(ds) != len(ks):
+        raise ValueError("unsupported resblock configuration")
+    s.n_resblock_kernels = len(ks)
+    for i, k in enumerate(ks):
+        s.resblock_kernel_sizes[i] = int(k)
+        for j in range(3):
+            s.resblock_dilations[i][j] = int(ds[i][j])
+    ur, uk = list(get(model, "upsample_rates")), list(get(model, "upsample_kernel_sizes"))
+    if len(ur) > 4 or len(ur) != len(uk):
+        raise ValueError("unsupported upsample configuration")
+    s.n_upsamples = len(ur)
+    for i in range(len(ur)):
+        s.upsample_rates[i] = int(ur[i])
+        s.upsample_kernel_sizes[i] = int(uk[i])
+    s.upsample_initial_channel = int(get(model, "upsample_initial_channel"))
+    s.zero_g = 1 if get(model, "zero_g", False) else 0
+    s.hop_length = int(get(data, "hop_length"))
+    return s
+
+
+class NativeConverter:
+    """Owns one ovc_ctx (one per device)."""
+
+    def __init__(self, hps, device_index: int):
+        self.lib = load_library()
+        self.hp = hparams_struct(hps)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.ovc_create(C.byref(self.hp), int(device_index), C.byref(h)), "ovc_create")
+        self.handle = h
+        self.device_index = int(device_index)
+        self.finalized = False
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ovc_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ---------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, "object"]) -> Tuple[list, list]:
+        """Feed a reference-schema state dict; returns (used_keys, ignored_keys)."""
+        import numpy as np
+        used, ignored = [], []
+        for k, v in sd.items():
+            a = v.detach().cpu().float().contiguous().numpy() if hasattr(v, "detach") else np.ascontiguousarray(v, dtype=np.float32)
+            if a.ndim == 0 or a.ndim > 4:
+                ignored.append(k)
+                continue
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            rc = self.lib.ovc_load_tensor(self.handle, k.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim)
+            _check(self.lib, rc, f"ovc_load_tensor({k})")
+            (ignored if rc == 1 else used).append(k)
+        self.finalized = False
+        return used, ignored
+
+    def finalize(self):
+        _check(self.lib, self.lib.ovc_finalize_weights(self.handle), "ovc_finalize_weights")
+        self.finalized = True
+
+    # ---- hot path --------------------------------------------------------------------------
+    def voice_conversion(self, spec, lengths, g_src, g_tgt, noise=None, tau: float = 0.3, seed: int = 0,
+                         ragged: bool = False, latents: bool = True, stream=None):
+        """spec [B,S,T] f32 cuda, lengths [B] i64 cuda, g_* [B,gin(,1)] f32 cuda.
+        Returns (o_hat [B,1,hop*T], (z, z_p, z_hat) or None).  Asynchronous on `stream`."""
+        import torch
+        assert spec.is_cuda and spec.dtype == torch.float32 and spec.is_contiguous()
+        assert lengths.is_cuda and lengths.dtype == torch.int64 and lengths.is_contiguous()
+        B, S, T = spec.shape
+        gs = g_src.reshape(B, -1).contiguous().float()
+        gt = g_tgt.reshape(B, -1).contiguous().float()
+        if noise is not None:
+            noise = noise.contiguous().float()
+            assert tuple(noise.shape) == (B, self.hp.inter_channels, T)
+        hop = self.hp.hop_length
+        o = torch.empty(B, 1, hop * T, device=spec.device, dtype=torch.float32)
+        lat = None
+        if latents:
+            lat = tuple(torch.empty(B, self.hp.inter_channels, T, device=spec.device, dtype=torch.float32)
+                        for _ in range(3))
+        st = stream if stream is not None else torch.cuda.current_stream(spec.device)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        rc = self.lib.ovc_voice_conversion(
+            self.handle, p(spec), p(lengths), p(gs), p(gt), p(noise), C.c_uint64(seed & (2 ** 64 - 1)),
+            C.c_float(tau), B, T, 1 if ragged else 0, p(o),
+            p(lat[0]) if lat else None, p(lat[1]) if lat else None, p(lat[2]) if lat else None,
+            C.c_void_p(st.cuda_stream))
+        _check(self.lib, rc, "ovc_voice_conversion")
+        return o, lat
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.ovc_last_launch_count(self.handle))
+
+    # ---- instrumentation -------------------------------------------------------------------
+    def profile_enable(self, on: bool):
+        _check(self.lib, self.lib.ovc_profile_enable(self.handle, 1 if on else 0), "ovc_profile_enable")
+
+    def profile_read(self):
+        ms, n, fl, by = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+        _check(self.lib, self.lib.ovc_profile_read(self.handle, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)),
+               "ovc_profile_read")
+        return dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+
+    def debug_enable(self, on: bool):
+        _check(self.lib, self.lib.ovc_debug_enable(self.handle, 1 if on else 0), "ovc_debug_enable")
+
+    def debug_fetch(self, name: str):
+        """Returns a numpy array [B, C, T] of the named tap of the last call."""
+        import numpy as np
+        shape = (C.c_int64 * 4)()
+        _check(self.lib, self.lib.ovc_debug_fetch(self.handle, name.encode(), None, 0, shape), "ovc_debug_fetch")
+        B, Cc, T, pitch = [int(v) for v in shape]
+        buf = np.empty((B, Cc, pitch), dtype=np.float32)
+        _check(self.lib, self.lib.ovc_debug_fetch(self.handle, name.encode(), buf.ctypes.data_as(C.c_void_p),
+                                                  buf.size, shape), "ovc_debug_fetch")
+        return buf[:, :, :T]

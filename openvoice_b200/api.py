@@ -1,0 +1,325 @@
+"""Drop-in for the tone-colour-converter half of the reference's ``openvoice/api.py``.
+
+Same classes, method names, arguments and return types as ``OpenVoiceBaseClass`` /
+``ToneColorConverter`` (openvoice/api.py:14-39, :101-201); ``self.model`` is a
+``NativeSynthesizer`` whose ``voice_conversion`` (the seam at openvoice/api.py:154) runs in
+libovc_b200.so.  Supersets of the reference: ``convert`` also accepts a NumPy waveform,
+``convert_batch`` converts a list of utterances in one launch sequence,
+``enable_watermark=False`` works (it raises TypeError in the reference).
+CUDA only: there is no CPU path.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import utils
+from ._native import NativeConverter
+from .mel_processing import spectrogram_torch
+from .ref_enc import ReferenceEncoder
+from .schema import hot_path_keys, ref_enc_keys
+
+AudioLike = Union[str, np.ndarray]
+
+
+def _load_audio(src: AudioLike, sr: int) -> np.ndarray:
+    """Stand-in for ``librosa.load(path, sr=sr)`` (openvoice/api.py:144): mono float32 at ``sr``.
+    Uses librosa when it is installed; otherwise .npy (already at ``sr``) and PCM/float .wav via
+    scipy, with polyphase resampling (not bit-identical to librosa's resampler -- third-party
+    arithmetic the reference does not pin)."""
+    if isinstance(src, np.ndarray):
+        return np.ascontiguousarray(src, dtype=np.float32).reshape(-1)
+    if src.endswith(".npy"):
+        return np.ascontiguousarray(np.load(src), dtype=np.float32).reshape(-1)
+    try:
+        import librosa  # type: ignore
+        return librosa.load(src, sr=sr)[0].astype(np.float32)
+    except ImportError:
+        pass
+    from scipy.io import wavfile
+    from scipy.signal import resample_poly
+    file_sr, data = wavfile.read(src)
+    if data.dtype.kind == "i":
+        data = data.astype(np.float32) / float(np.iinfo(data.dtype).max + 1)
+    elif data.dtype.kind == "u":
+        data = (data.astype(np.float32) - 128.0) / 128.0
+    data = data.astype(np.float32)
+    if data.ndim == 2:
+        data = data.mean(axis=1)
+    if file_sr != sr:
+        from math import gcd
+        g = gcd(int(file_sr), int(sr))
+        data = resample_poly(data, sr // g, file_sr // g).astype(np.float32)
+    return np.ascontiguousarray(data)
+
+
+def _write_audio(path: str, audio: np.ndarray, sr: int) -> None:
+    """Stand-in for ``soundfile.write`` (openvoice/api.py:160)."""
+    if path.endswith(".npy"):
+        np.save(path, audio)
+        return
+    try:
+        import soundfile  # type: ignore
+        soundfile.write(path, audio, sr)
+    except ImportError:
+        from scipy.io import wavfile
+        wavfile.write(path, sr, audio.astype(np.float32))
+
+
+class NativeSynthesizer:
+    """Stands where ``SynthesizerTrn`` stands in the reference (``converter.model``) for the
+    ``n_speakers == 0`` converter (openvoice/models.py:399-465): ``voice_conversion``,
+    ``ref_enc``, ``load_state_dict``, ``eval``, ``zero_g``."""
+
+    def __init__(self, hps, device: str):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("openvoice_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.device = dev
+        self.hps = hps
+        self.zero_g = bool(getattr(hps.model, "zero_g", False))
+        self.n_speakers = int(getattr(hps.data, "n_speakers", 0))
+        if self.n_speakers != 0:
+            raise ValueError("only the tone-colour converter (n_speakers == 0) is implemented; the V1 "
+                             "base-speaker TTS front half is out of this build's scope")
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.native = NativeConverter(hps, index)
+        self.spec_channels = hps.data.filter_length // 2 + 1
+        self.ref_enc = ReferenceEncoder(self.spec_channels, int(getattr(hps.model, "gin_channels", 256)))
+        self._expected = hot_path_keys(hps) + ref_enc_keys()
+
+    # nn.Module-ish surface used by callers of the reference
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if torch.device(device) != self.device and torch.device(device).type != "cuda":
+            raise RuntimeError("CUDA only")
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = False):
+        """Returns (missing_keys, unexpected_keys) like torch with strict=False.  Unlike the
+        reference, a checkpoint that lacks hot-path tensors is an error (the reference would
+        silently keep random weights)."""
+        provided = set(state_dict.keys())
+        expected = set(self._expected)
+        missing = sorted(expected - provided)
+        unexpected = sorted(provided - expected)
+        self.native.load_state_dict(state_dict)
+        self.native.finalize()          # raises OvcError naming the first missing hot-path key
+        self.ref_enc.load_state_dict(state_dict, self.device)
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"missing keys {missing}, unexpected keys {unexpected}")
+        return missing, unexpected
+
+    @torch.no_grad()
+    def voice_conversion(self, y, y_lengths, sid_src, sid_tgt, tau: float = 1.0, noise=None,
+                         ragged: bool = False, seed: Optional[int] = None, latents: bool = True):
+        """(o_hat, y_mask, (z, z_p, z_hat)) = SynthesizerTrn.voice_conversion
+        (openvoice/models.py:492-499).  ``noise`` ([B,192,T]) replaces the reference's
+        ``randn_like``; when None, Philox normals are drawn in-kernel from ``seed`` (default: a
+        draw from torch's global CPU generator, so ``torch.manual_seed`` makes runs repeatable).
+        ``ragged=True`` converts every item at its exact length (what ``convert`` does)."""
+        y = y.to(self.device, torch.float32).contiguous()
+        B, _, T = y.shape
+        y_lengths = y_lengths.to(self.device, torch.int64).contiguous()
+        sid_src = self._expand_se(sid_src, B)
+        sid_tgt = self._expand_se(sid_tgt, B)
+        if noise is None and seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if noise is not None:
+            noise = noise.to(self.device, torch.float32)
+        o, lat = self.native.voice_conversion(y, y_lengths, sid_src, sid_tgt, noise=noise, tau=float(tau),
+                                              seed=seed or 0, ragged=ragged, latents=latents)
+        y_mask = (torch.arange(T, device=self.device)[None, :] < y_lengths[:, None]).unsqueeze(1).to(torch.float32)
+        return o, y_mask, lat
+
+    def _expand_se(self, se, B):
+        se = se.to(self.device, torch.float32).reshape(se.shape[0], -1)
+        if se.shape[0] == 1 and B > 1:
+            se = se.expand(B, -1)
+        if se.shape[0] != B:
+            raise ValueError(f"speaker embedding batch {se.shape[0]} does not match batch {B}")
+        return se.contiguous()
+
+
+class OpenVoiceBaseClass(object):
+    """openvoice/api.py:14-39."""
+
+    def __init__(self, config_path, device="cuda:0"):
+        if "cuda" in device:
+            assert torch.cuda.is_available()
+        hps = utils.get_hparams_from_file(config_path)
+        self.model = NativeSynthesizer(hps, device).eval()
+        self.hps = hps
+        self.device = device
+
+    def load_ckpt(self, ckpt_path):
+        checkpoint_dict = torch.load(ckpt_path, map_location=torch.device("cpu"))
+        a, b = self.model.load_state_dict(checkpoint_dict["model"], strict=False)
+        print("Loaded checkpoint '{}'".format(ckpt_path))
+        print("missing/unexpected keys:", a, b)
+
+
+class ToneColorConverter(OpenVoiceBaseClass):
+    """openvoice/api.py:101-201."""
+
+    def __init__(self, *args, **kwargs):
+        enable_watermark = kwargs.pop("enable_watermark", True)
+        super().__init__(*args, **kwargs)
+        self.watermark_model = None
+        if enable_watermark:
+            try:
+                import wavmark  # type: ignore
+                self.watermark_model = wavmark.load_model().to(self.device)
+            except ImportError:
+                print("wavmark is not installed: watermarking disabled")
+        self.version = getattr(self.hps, "_version_", "v1")
+
+    # ------------------------------------------------------------------ speaker embedding
+    def extract_se(self, ref_wav_list, se_save_path=None):
+        """openvoice/api.py:114-139: mean ReferenceEncoder embedding over the given clips,
+        shape [1, gin, 1]."""
+        if isinstance(ref_wav_list, (str, np.ndarray)):
+            ref_wav_list = [ref_wav_list]
+        hps = self.hps
+        gs = []
+        for fname in ref_wav_list:
+            audio_ref = _load_audio(fname, hps.data.sampling_rate)
+            y = torch.from_numpy(audio_ref).to(self.device).unsqueeze(0)
+            y = spectrogram_torch(y, hps.data.filter_length, hps.data.sampling_rate, hps.data.hop_length,
+                                  hps.data.win_length, center=False)
+            g = self.model.ref_enc(y.transpose(1, 2)).unsqueeze(-1)
+            gs.append(g.detach())
+        gs = torch.stack(gs).mean(0)
+        if se_save_path is not None:
+            os.makedirs(os.path.dirname(se_save_path), exist_ok=True)
+            torch.save(gs.cpu(), se_save_path)
+        return gs
+
+    # ------------------------------------------------------------------ conversion
+    def convert(self, audio_src_path, src_se, tgt_se, output_path=None, tau=0.3, message="default",
+                noise=None):
+        """openvoice/api.py:141-160.  Returns float32 samples (256 * (L // 256) of them) or writes
+        ``output_path``.  ``noise`` ([1,192,T]) optionally replaces the random draw (tests)."""
+        audio = self.convert_batch([audio_src_path], src_se, tgt_se, tau=tau, messages=[message],
+                                   noise=None if noise is None else [noise])[0]
+        if output_path is None:
+            return audio
+        _write_audio(output_path, audio, self.hps.data.sampling_rate)
+
+    @torch.no_grad()
+    def convert_batch(self, audios: Sequence[AudioLike], src_se, tgt_se, tau: float = 0.3,
+                      messages: Optional[Sequence[str]] = None, noise: Optional[Sequence] = None,
+                      max_batch: int = 64) -> List[np.ndarray]:
+        """Convert a list of utterances (paths or waveforms at the model sampling rate); every item
+        gets exactly what ``convert`` would return for it alone.  ``src_se`` / ``tgt_se`` are either
+        one [1,gin,1] embedding for all items or a sequence of per-item embeddings."""
+        hps = self.hps
+        n = len(audios)
+        waves = [_load_audio(a, hps.data.sampling_rate) for a in audios]
+        src = self._stack_se(src_se, n)
+        tgt = self._stack_se(tgt_se, n)
+        out: List[Optional[np.ndarray]] = [None] * n
+        order = sorted(range(n), key=lambda i: -len(waves[i]))     # similar lengths share a launch
+        hop = hps.data.hop_length
+        for lo in range(0, n, max_batch):
+            idx = order[lo: lo + max_batch]
+            res = self._convert_chunk([waves[i] for i in idx], src[idx], tgt[idx], tau,
+                                      None if noise is None else [noise[i] for i in idx])
+            for i, a in zip(idx, res):
+                msg = messages[i] if messages is not None else "default"
+                out[i] = self.add_watermark(a, msg)
+        return out  # type: ignore[return-value]
+
+    def _stack_se(self, se, n):
+        if isinstance(se, (list, tuple)):
+            se = torch.cat([s.reshape(1, -1) for s in se], 0)
+        se = se.to(self.device, torch.float32).reshape(se.shape[0], -1)
+        if se.shape[0] == 1:
+            se = se.expand(n, -1)
+        assert se.shape[0] == n, "one speaker embedding per utterance (or a single one for all)"
+        return se
+
+    def _convert_chunk(self, waves, src, tgt, tau, noise):
+        hps = self.hps
+        hop = hps.data.hop_length
+        B = len(waves)
+        frames = [len(w) // hop for w in waves]
+        if min(frames) < 1:
+            raise ValueError("audio shorter than one hop")
+        Tmax = max(frames)
+        dev = self.device
+        # host -> device: one pinned staging buffer, one copy
+        Lmax = max(len(w) for w in waves)
+        stage = torch.zeros(B, Lmax, dtype=torch.float32).pin_memory()
+        for b, w in enumerate(waves):
+            stage[b, : len(w)] = torch.from_numpy(w)
+        wav = stage.to(dev, non_blocking=True)
+        spec = torch.zeros(B, hps.data.filter_length // 2 + 1, Tmax, device=dev, dtype=torch.float32)
+        if len(set(len(w) for w in waves)) == 1:
+            spec = spectrogram_torch(wav, hps.data.filter_length, hps.data.sampling_rate, hop,
+                                     hps.data.win_length, center=False).contiguous()
+        else:   # reflect padding happens at each utterance's own end
+            for b, w in enumerate(waves):
+                s = spectrogram_torch(wav[b: b + 1, : len(w)], hps.data.filter_length, hps.data.sampling_rate,
+                                      hop, hps.data.win_length, center=False)
+                spec[b, :, : s.shape[2]] = s[0]
+        lengths = torch.tensor(frames, dtype=torch.int64).to(dev, non_blocking=True)
+        nz = None
+        if noise is not None:
+            nz = torch.zeros(B, hps.model.inter_channels, Tmax, device=dev, dtype=torch.float32)
+            for b, q in enumerate(noise):
+                q = q.reshape(hps.model.inter_channels, -1)
+                nz[b, :, : q.shape[1]] = q.to(dev)
+        o, _, _ = self.model.voice_conversion(spec, lengths, src, tgt, tau=tau, noise=nz, ragged=True,
+                                              latents=False)
+        host = torch.empty(o.shape, dtype=torch.float32).pin_memory()
+        host.copy_(o, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        audio = host[:, 0].numpy()
+        return [audio[b, : frames[b] * hop].copy() for b in range(B)]
+
+    # ------------------------------------------------------------------ watermark (third-party model)
+    def add_watermark(self, audio, message):
+        """openvoice/api.py:162-184 (wavmark encoder on 16000-sample chunks at 0 and 32000)."""
+        if self.watermark_model is None:
+            return audio
+        device = self.device
+        bits = utils.string_to_bits(message).reshape(-1)
+        n_repeat = len(bits) // 32
+        K = 16000
+        coeff = 2
+        for n in range(n_repeat):
+            trunck = audio[(coeff * n) * K: (coeff * n + 1) * K]
+            if len(trunck) != K:
+                print("Audio too short, fail to add watermark")
+                break
+            message_npy = bits[n * 32: (n + 1) * 32]
+            with torch.no_grad():
+                signal = torch.FloatTensor(trunck).to(device)[None]
+                message_tensor = torch.FloatTensor(message_npy).to(device)[None]
+                signal_wmd_tensor = self.watermark_model.encode(signal, message_tensor)
+                signal_wmd_npy = signal_wmd_tensor.detach().cpu().squeeze()
+            audio[(coeff * n) * K: (coeff * n + 1) * K] = signal_wmd_npy
+        return audio
+
+    def detect_watermark(self, audio, n_repeat):
+        """openvoice/api.py:186-201."""
+        bits = []
+        K = 16000
+        coeff = 2
+        for n in range(n_repeat):
+            trunck = audio[(coeff * n) * K: (coeff * n + 1) * K]
+            if len(trunck) != K:
+                print("Audio too short, fail to detect watermark")
+                return "Fail"
+            with torch.no_grad():
+                signal = torch.FloatTensor(trunck).to(self.device).unsqueeze(0)
+                message_decoded_npy = (self.watermark_model.decode(signal) >= 0.5).int().detach().cpu().numpy().squeeze()
+            bits.append(message_decoded_npy)
+        bits = np.stack(bits).reshape(-1, 8)
+        return utils.bits_to_string(bits)

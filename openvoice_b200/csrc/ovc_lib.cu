@@ -1,0 +1,894 @@
+// ovc_lib.cu -- host side of libovc_b200.so: context, checkpoint ingestion (weight-norm folding,
+// Flip absorption, kernel-layout packing), workspace arena, the launch sequence of
+// SynthesizerTrn.voice_conversion (openvoice/models.py:492-499) and the C ABI of include/ovc.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ovc.h"
+#include "ovc_small.cuh"
+#include "ovc_variants.h"
+
+namespace ovc {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(expr)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(OVC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                      \
+  } while (0)
+
+static const VariantInfo kInfo[V_COUNT] = {
+#define X(name, K, D, WM, WN, CI, EPI, NG, XA)                                                    \
+  {#name, K, D, 32 * WM, 64 * WN, CI, EPI, 32 * WM * WN, ConvCfg<K, D, WM, WN, CI, EPI, NG, XA>::SMEM_BYTES},
+    OVC_VARIANTS_ALL(X)
+#undef X
+};
+static const LaunchFn kLaunch[V_COUNT] = {
+#define X(name, K, D, WM, WN, CI, EPI, NG, XA) launch_##name,
+    OVC_VARIANTS_ALL(X)
+#undef X
+};
+static const PrepareFn kPrepare[V_COUNT] = {
+#define X(name, K, D, WM, WN, CI, EPI, NG, XA) prepare_##name,
+    OVC_VARIANTS_ALL(X)
+#undef X
+};
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// one convolution as the kernels see it
+struct ConvLayer {
+  int variant = -1;
+  int rows = 0;        // packed output rows (multiple of CO_T)
+  int row_tiles = 0;
+  int cin = 0;         // real input channels
+  int n_chunks = 0;
+  size_t w_off = 0;    // float offsets into the device weight arena
+  size_t b_off = 0;
+  int K = 1;           // true taps / channels, for FLOP accounting
+  int cout = 0;
+};
+
+struct WNLayers {
+  std::vector<ConvLayer> in, rs;
+};
+
+struct DebugBuf {
+  float* d = nullptr;
+  int64_t shape[4] = {0, 0, 0, 0};
+  size_t floats = 0;
+};
+
+}  // namespace ovc
+
+using namespace ovc;
+
+struct ovc_ctx {
+  ovc_hparams hp{};
+  int device = 0;
+  int sm_count = 0;
+  std::map<std::string, HostTensor> sd;
+  bool finalized = false;
+
+  // device weights
+  float* d_w = nullptr;
+  size_t w_floats = 0;
+  std::vector<float> h_w;   // staging while packing
+
+  // layers
+  ConvLayer enc_pre, enc_proj;
+  WNLayers enc_wn;
+  ConvLayer flow_pre[4], flow_post[4];
+  WNLayers flow_wn[4];
+  ConvLayer dec_pre, dec_ups[4];
+  ConvLayer rb_c1[12][3], rb_c2[12][3];
+  size_t post_w_off = 0;
+  // cond mat-vec
+  size_t cond_w_off = 0, cond_b_off = 0;
+  int* d_cond_wrow = nullptr;
+  int* d_cond_sel = nullptr;
+  int cond_rows_out = 0;
+  int cond_off_enc = 0, cond_off_fsrc = 0, cond_off_ftgt = 0, cond_off_dec = 0;
+
+  // workspace
+  float* d_ws = nullptr;
+  size_t ws_floats = 0;
+
+  // profiling
+  bool prof = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  double prof_ms = 0, prof_flops = 0, prof_bytes = 0;
+  int64_t prof_launches = 0;
+  std::vector<double> ev_flops, ev_bytes;
+
+  // debug taps
+  bool debug = false;
+  std::map<std::string, DebugBuf> taps;
+
+  int launches = 0;
+};
+
+namespace ovc {
+
+static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+static const HostTensor* find(const ovc_ctx* c, const std::string& k) {
+  auto it = c->sd.find(k);
+  return it == c->sd.end() ? nullptr : &it->second;
+}
+
+// effective weight of a (possibly weight-normed) conv: g * v / ||v|| over dims != 0
+// (torch.nn.utils.weight_norm dim=0; modules.py:160,172,182, models.py:247)
+static int effective_weight(const ovc_ctx* c, const std::string& prefix, HostTensor* out, std::string* missing) {
+  if (const HostTensor* w = find(c, prefix + ".weight")) {
+    *out = *w;
+    return 0;
+  }
+  const HostTensor* v = find(c, prefix + ".weight_v");
+  const HostTensor* g = find(c, prefix + ".weight_g");
+  if (!v) { *missing = prefix + ".weight_v"; return -1; }
+  if (!g) { *missing = prefix + ".weight_g"; return -1; }
+  *out = *v;
+  const int64_t d0 = v->shape[0];
+  const int64_t inner = v->numel() / d0;
+  if (g->numel() != d0) { *missing = prefix + ".weight_g(shape)"; return -1; }
+  for (int64_t i = 0; i < d0; ++i) {
+    double ss = 0;
+    for (int64_t j = 0; j < inner; ++j) { const double q = v->data[i * inner + j]; ss += q * q; }
+    const float scale = g->data[i] / (float)std::sqrt(ss);
+    for (int64_t j = 0; j < inner; ++j) out->data[i * inner + j] = v->data[i * inner + j] * scale;
+  }
+  return 0;
+}
+
+// append a packed conv to the staging arena.  wfun(row_packed, ci, k) -> weight; bfun(row) -> bias
+template <class WF, class BF>
+static ConvLayer pack_conv(ovc_ctx* c, int variant, int rows, int cin, WF wfun, BF bfun, int bias_rows,
+                           int trueK, int cout) {
+  const VariantInfo& vi = kInfo[variant];
+  ConvLayer L;
+  L.variant = variant;
+  L.rows = rows;
+  L.row_tiles = rows / vi.CO_T;
+  L.cin = cin;
+  L.n_chunks = (cin + vi.CI_CH - 1) / vi.CI_CH;
+  L.K = trueK;
+  L.cout = cout;
+  const int cin_pad = L.n_chunks * vi.CI_CH;
+  L.w_off = round_up(c->h_w.size(), 64);   // 256-byte aligned blobs (TMA bulk needs 16)
+  c->h_w.resize(L.w_off + (size_t)L.row_tiles * cin_pad * vi.K * vi.CO_T, 0.f);
+  float* dst = c->h_w.data() + L.w_off;
+  for (int rt = 0; rt < L.row_tiles; ++rt)
+    for (int ci = 0; ci < cin_pad; ++ci)
+      for (int k = 0; k < vi.K; ++k)
+        for (int r = 0; r < vi.CO_T; ++r)
+          dst[(((size_t)rt * cin_pad + ci) * vi.K + k) * vi.CO_T + r] =
+              ci < cin ? wfun(rt * vi.CO_T + r, ci, k) : 0.f;
+  L.b_off = round_up(c->h_w.size(), 64);
+  c->h_w.resize(L.b_off + bias_rows, 0.f);
+  for (int r = 0; r < bias_rows; ++r) c->h_w[L.b_off + r] = bfun(r);
+  return L;
+}
+
+// packed row -> original row for the paired (tanh|sigmoid, m|logs) layouts: a thread's 8 rows
+// are 4 channels of the first half followed by the same 4 channels of the second half
+static inline int paired_row(int p, int half) {
+  const int q = p / 8, r = p % 8;
+  return r < 4 ? 4 * q + r : half + 4 * q + (r - 4);
+}
+
+static int dec_variant(int C, int K, int D) {
+  const int cls = C >= 128 ? 0 : (C == 64 ? 1 : 2);
+  static const int tab[3][3][3] = {
+      {{V_A_K3D1, V_A_K3D3, V_A_K3D5}, {V_A_K7D1, V_A_K7D3, V_A_K7D5}, {V_A_K11D1, V_A_K11D3, V_A_K11D5}},
+      {{V_B_K3D1, V_B_K3D3, V_B_K3D5}, {V_B_K7D1, V_B_K7D3, V_B_K7D5}, {V_B_K11D1, V_B_K11D3, V_B_K11D5}},
+      {{V_C_K3D1, V_C_K3D3, V_C_K3D5}, {V_C_K7D1, V_C_K7D3, V_C_K7D5}, {V_C_K11D1, V_C_K11D3, V_C_K11D5}}};
+  const int ki = K == 3 ? 0 : (K == 7 ? 1 : 2);
+  const int di = D == 1 ? 0 : (D == 3 ? 1 : 2);
+  return tab[cls][ki][di];
+}
+
+static int validate_hparams(const ovc_hparams* hp) {
+  if (hp->inter_channels != 192 || hp->hidden_channels != 192)
+    return fail(OVC_ERR_INVALID, "kernels are specialised for inter_channels = hidden_channels = 192 (got %d, %d)",
+                hp->inter_channels, hp->hidden_channels);
+  if (hp->spec_channels < 1 || hp->spec_channels > 4096) return fail(OVC_ERR_INVALID, "bad spec_channels %d", hp->spec_channels);
+  if (hp->gin_channels < 1 || hp->gin_channels > 4096) return fail(OVC_ERR_INVALID, "bad gin_channels %d", hp->gin_channels);
+  if (hp->resblock != 1) return fail(OVC_ERR_INVALID, "only resblock \"1\" (ResBlock1) is supported, got %d", hp->resblock);
+  if (hp->n_resblock_kernels != 3 || hp->resblock_kernel_sizes[0] != 3 || hp->resblock_kernel_sizes[1] != 7 ||
+      hp->resblock_kernel_sizes[2] != 11)
+    return fail(OVC_ERR_INVALID, "resblock_kernel_sizes must be [3,7,11]");
+  for (int j = 0; j < 3; ++j)
+    if (hp->resblock_dilations[j][0] != 1 || hp->resblock_dilations[j][1] != 3 || hp->resblock_dilations[j][2] != 5)
+      return fail(OVC_ERR_INVALID, "resblock_dilation_sizes must be [[1,3,5]]*3");
+  static const int ur[4] = {8, 8, 2, 2}, uk[4] = {16, 16, 4, 4};
+  if (hp->n_upsamples != 4) return fail(OVC_ERR_INVALID, "need 4 upsample stages");
+  for (int i = 0; i < 4; ++i)
+    if (hp->upsample_rates[i] != ur[i] || hp->upsample_kernel_sizes[i] != uk[i])
+      return fail(OVC_ERR_INVALID, "upsample_rates/kernel_sizes must be [8,8,2,2]/[16,16,4,4]");
+  if (hp->upsample_initial_channel != 512) return fail(OVC_ERR_INVALID, "upsample_initial_channel must be 512");
+  if (hp->hop_length != 256) return fail(OVC_ERR_INVALID, "hop_length must be 256");
+  return OVC_OK;
+}
+
+static bool key_is_hot(const std::string& k) {
+  return k.rfind("enc_q.", 0) == 0 || k.rfind("flow.", 0) == 0 || k.rfind("dec.", 0) == 0;
+}
+
+static int pack_wn(ovc_ctx* c, const std::string& prefix, int n_layers, WNLayers* out, std::string* missing) {
+  const int H = 192;
+  for (int i = 0; i < n_layers; ++i) {
+    HostTensor w;
+    const std::string pin = prefix + ".in_layers." + std::to_string(i);
+    if (effective_weight(c, pin, &w, missing)) return -1;
+    if (w.shape.size() != 3 || w.shape[0] != 2 * H || w.shape[1] != H || w.shape[2] != 5) { *missing = pin + "(shape)"; return -1; }
+    // bias of the in_layer is folded into the per-batch conditioning vector (cond kernel)
+    out->in.push_back(pack_conv(
+        c, V_WN_IN, 2 * H, H,
+        [&](int p, int ci, int k) { return w.data[((size_t)paired_row(p, H) * H + ci) * 5 + k]; },
+        [&](int) { return 0.f; }, 0, 5, 2 * H));
+    const std::string prs = prefix + ".res_skip_layers." + std::to_string(i);
+    HostTensor r;
+    if (effective_weight(c, prs, &r, missing)) return -1;
+    const HostTensor* rb = find(c, prs + ".bias");
+    if (!rb) { *missing = prs + ".bias"; return -1; }
+    const int rows = (i < n_layers - 1) ? 2 * H : H;
+    if (r.shape[0] != rows || r.shape[1] != H) { *missing = prs + "(shape)"; return -1; }
+    out->rs.push_back(pack_conv(
+        c, V_WN_RS, rows, H, [&](int p, int ci, int) { return r.data[(size_t)p * H + ci]; },
+        [&](int p) { return rb->data[p]; }, rows, 1, rows));
+  }
+  return 0;
+}
+
+static int finalize(ovc_ctx* c) {
+  const ovc_hparams& hp = c->hp;
+  const int H = 192, S = hp.spec_channels, G = hp.gin_channels;
+  std::string miss;
+  c->h_w.clear();
+#define NEED(ptr, key)                                                                     \
+  const HostTensor* ptr = find(c, key);                                                    \
+  if (!ptr) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing", std::string(key).c_str())
+#define WEFF(var, prefix)                                                                  \
+  HostTensor var;                                                                          \
+  if (effective_weight(c, prefix, &var, &miss)) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str())
+
+  // ---- posterior encoder (models.py:182-221)
+  {
+    NEED(w, "enc_q.pre.weight");
+    NEED(b, "enc_q.pre.bias");
+    if (w->shape.size() != 3 || w->shape[0] != H || w->shape[1] != S) return fail(OVC_ERR_INVALID, "enc_q.pre.weight has the wrong shape");
+    c->enc_pre = pack_conv(c, V_ENC_PRE, H, S, [&](int p, int ci, int) { return w->data[(size_t)p * S + ci]; },
+                           [&](int p) { return b->data[p]; }, H, 1, H);
+    if (pack_wn(c, "enc_q.enc", 16, &c->enc_wn, &miss)) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    NEED(pw, "enc_q.proj.weight");
+    NEED(pb, "enc_q.proj.bias");
+    if (pw->shape[0] != 2 * H || pw->shape[1] != H) return fail(OVC_ERR_INVALID, "enc_q.proj.weight has the wrong shape");
+    c->enc_proj = pack_conv(c, V_ENC_PROJ, 2 * H, H,
+                            [&](int p, int ci, int) { return pw->data[(size_t)paired_row(p, H) * H + ci]; },
+                            [&](int p) { return pb->data[paired_row(p, H)]; }, 2 * H, 1, 2 * H);
+  }
+  // ---- flow: 4 x (coupling, Flip) (models.py:385-388).  The Flips are absorbed: coupling f sees
+  // the channel-reversed tensor iff f is odd, in both directions, so its `pre` reads the physical
+  // upper half with reversed columns and its `post` writes the physical lower half with reversed rows.
+  for (int f = 0; f < 4; ++f) {
+    const std::string p = "flow.flows." + std::to_string(2 * f);
+    const bool flipped = f & 1;
+    NEED(w, p + ".pre.weight");
+    NEED(b, p + ".pre.bias");
+    if (w->shape[0] != H || w->shape[1] != 96) return fail(OVC_ERR_INVALID, "%s.pre.weight has the wrong shape", p.c_str());
+    c->flow_pre[f] = pack_conv(
+        c, V_FLOW_PRE, H, 96,
+        [&](int r, int ci, int) { return w->data[(size_t)r * 96 + (flipped ? 95 - ci : ci)]; },
+        [&](int r) { return b->data[r]; }, H, 1, H);
+    if (pack_wn(c, p + ".enc", 4, &c->flow_wn[f], &miss)) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    NEED(pw, p + ".post.weight");
+    NEED(pb, p + ".post.bias");
+    if (pw->shape[0] != 96 || pw->shape[1] != H) return fail(OVC_ERR_INVALID, "%s.post.weight has the wrong shape (mean_only couplings only)", p.c_str());
+    c->flow_post[f] = pack_conv(
+        c, V_FLOW_POST, 96, H,
+        [&](int r, int ci, int) { return pw->data[(size_t)(flipped ? 95 - r : r) * H + ci]; },
+        [&](int r) { return pb->data[flipped ? 95 - r : r]; }, 96, 1, 96);
+  }
+  // ---- generator (models.py:224-291)
+  NEED(cpb, "dec.conv_pre.bias");
+  {
+    NEED(w, "dec.conv_pre.weight");
+    if (w->shape[0] != 512 || w->shape[1] != H || w->shape[2] != 7) return fail(OVC_ERR_INVALID, "dec.conv_pre.weight has the wrong shape");
+    // bias comes per batch item from the cond kernel (conv_pre.bias + cond(g))
+    c->dec_pre = pack_conv(c, V_A_K7D1, 512, H, [&](int r, int ci, int k) { return w->data[((size_t)r * H + ci) * 7 + k]; },
+                           [&](int) { return 0.f; }, 0, 7, 512);
+  }
+  int ch = 512;
+  for (int i = 0; i < 4; ++i) {
+    const int s = hp.upsample_rates[i], kk = hp.upsample_kernel_sizes[i], pad = (kk - s) / 2;
+    const int cin = ch, cout = ch / 2;
+    const std::string p = "dec.ups." + std::to_string(i);
+    WEFF(w, p);   // [cin][cout][kk], weight-norm over dim 0 = cin
+    NEED(b, p + ".bias");
+    if (w.shape[0] != cin || w.shape[1] != cout || w.shape[2] != kk) return fail(OVC_ERR_INVALID, "%s weight has the wrong shape", p.c_str());
+    const int variant = s == 8 ? V_UPS8_A : (cout * s >= 128 ? V_UPS2_A : V_UPS2_B);
+    // polyphase: out[co, s*n+ph] = sum_ci sum_m x[ci, n-m] * W[ci, co, s*m + ph + pad];
+    // packed row = co*s + ph, tap 0/1/2 <-> x[n-1], x[n], x[n+1] <-> m = 1, 0, -1
+    c->dec_ups[i] = pack_conv(
+        c, variant, cout * s, cin,
+        [&](int row, int ci, int tap) {
+          const int co = row / s, ph = row % s;
+          const int kidx = s * (1 - tap) + ph + pad;
+          return (kidx >= 0 && kidx < kk) ? w.data[((size_t)ci * cout + co) * kk + kidx] : 0.f;
+        },
+        [&](int co) { return b->data[co]; }, cout, 2, cout);
+    ch = cout;
+    for (int j = 0; j < 3; ++j) {
+      const int K = hp.resblock_kernel_sizes[j];
+      const int rbi = i * 3 + j;
+      for (int d = 0; d < 3; ++d) {
+        for (int which = 0; which < 2; ++which) {
+          const std::string q = "dec.resblocks." + std::to_string(rbi) + (which ? ".convs2." : ".convs1.") + std::to_string(d);
+          WEFF(rw, q);
+          NEED(rbias, q + ".bias");
+          if (rw.shape[0] != ch || rw.shape[1] != ch || rw.shape[2] != K) return fail(OVC_ERR_INVALID, "%s weight has the wrong shape", q.c_str());
+          const int dil = which ? 1 : hp.resblock_dilations[j][d];
+          ConvLayer L = pack_conv(c, dec_variant(ch, K, dil), ch, ch,
+                                  [&](int r, int ci, int k) { return rw.data[((size_t)r * ch + ci) * K + k]; },
+                                  [&](int r) { return rbias->data[r]; }, ch, K, ch);
+          (which ? c->rb_c2 : c->rb_c1)[rbi][d] = L;
+        }
+      }
+    }
+  }
+  {
+    NEED(w, "dec.conv_post.weight");
+    if (w->shape[0] != 1 || w->shape[1] != 32 || w->shape[2] != 7) return fail(OVC_ERR_INVALID, "dec.conv_post.weight has the wrong shape");
+    c->post_w_off = round_up(c->h_w.size(), 64);
+    c->h_w.resize(c->post_w_off + 32 * 7);
+    std::copy(w->data.begin(), w->data.end(), c->h_w.begin() + c->post_w_off);
+  }
+  // ---- speaker conditioning mat-vec: stack cond_layer of enc_q, of the 4 couplings and dec.cond
+  std::vector<int> wrow, sel;
+  std::vector<float> cbias;
+  {
+    std::vector<float> cw;
+    auto add_wn = [&](const std::string& prefix, int n_layers, int first_row, int selv, bool add_matrix) -> int {
+      HostTensor w;
+      if (effective_weight(c, prefix + ".cond_layer", &w, &miss)) return -1;
+      const HostTensor* cb = find(c, prefix + ".cond_layer.bias");
+      if (!cb) { miss = prefix + ".cond_layer.bias"; return -1; }
+      if (w.shape[0] != 2 * H * n_layers || w.shape[1] != G) { miss = prefix + ".cond_layer(shape)"; return -1; }
+      if (add_matrix) cw.insert(cw.end(), w.data.begin(), w.data.end());
+      for (int l = 0; l < n_layers; ++l) {
+        const HostTensor* ib = find(c, prefix + ".in_layers." + std::to_string(l) + ".bias");
+        if (!ib) { miss = prefix + ".in_layers." + std::to_string(l) + ".bias"; return -1; }
+        for (int p = 0; p < 2 * H; ++p) {
+          const int o = paired_row(p, H);
+          wrow.push_back(first_row + l * 2 * H + o);
+          sel.push_back(selv);
+          cbias.push_back(cb->data[l * 2 * H + o] + ib->data[o]);
+        }
+      }
+      return 0;
+    };
+    c->cond_off_enc = 0;
+    if (add_wn("enc_q.enc", 16, 0, hp.zero_g ? 0 : 1, true)) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    c->cond_off_fsrc = (int)wrow.size();
+    for (int f = 0; f < 4; ++f)
+      if (add_wn("flow.flows." + std::to_string(2 * f) + ".enc", 4, 16 * 2 * H + f * 4 * 2 * H, 1, true))
+        return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    c->cond_off_ftgt = (int)wrow.size();
+    for (int f = 0; f < 4; ++f)
+      if (add_wn("flow.flows." + std::to_string(2 * f) + ".enc", 4, 16 * 2 * H + f * 4 * 2 * H, 2, false))
+        return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    c->cond_off_dec = (int)wrow.size();
+    NEED(dw, "dec.cond.weight");
+    NEED(db, "dec.cond.bias");
+    if (dw->shape[0] != 512 || dw->shape[1] != G) return fail(OVC_ERR_INVALID, "dec.cond.weight has the wrong shape");
+    const int dec_first = (int)(cw.size() / G);
+    cw.insert(cw.end(), dw->data.begin(), dw->data.end());
+    for (int r = 0; r < 512; ++r) {
+      wrow.push_back(dec_first + r);
+      sel.push_back(hp.zero_g ? 0 : 2);
+      cbias.push_back(db->data[r] + cpb->data[r]);
+    }
+    c->cond_rows_out = (int)wrow.size();
+    c->cond_w_off = round_up(c->h_w.size(), 64);
+    c->h_w.resize(c->cond_w_off + cw.size());
+    std::copy(cw.begin(), cw.end(), c->h_w.begin() + c->cond_w_off);
+    c->cond_b_off = round_up(c->h_w.size(), 64);
+    c->h_w.resize(c->cond_b_off + cbias.size());
+    std::copy(cbias.begin(), cbias.end(), c->h_w.begin() + c->cond_b_off);
+  }
+#undef NEED
+#undef WEFF
+  // ---- upload
+  CK(cudaSetDevice(c->device));
+  if (c->d_w) { cudaFree(c->d_w); c->d_w = nullptr; }
+  c->w_floats = c->h_w.size();
+  CK(cudaMalloc(&c->d_w, c->w_floats * sizeof(float)));
+  CK(cudaMemcpy(c->d_w, c->h_w.data(), c->w_floats * sizeof(float), cudaMemcpyHostToDevice));
+  if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
+  if (c->d_cond_sel) cudaFree(c->d_cond_sel);
+  CK(cudaMalloc(&c->d_cond_wrow, wrow.size() * sizeof(int)));
+  CK(cudaMalloc(&c->d_cond_sel, sel.size() * sizeof(int)));
+  CK(cudaMemcpy(c->d_cond_wrow, wrow.data(), wrow.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_cond_sel, sel.data(), sel.size() * sizeof(int), cudaMemcpyHostToDevice));
+  c->h_w.clear();
+  c->h_w.shrink_to_fit();
+  c->sd.clear();
+  for (int v = 0; v < V_COUNT; ++v) CK(kPrepare[v]());
+  c->finalized = true;
+  return OVC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------
+struct WsLayout {
+  int P;   // frame pitch (multiple of 4)
+  size_t cond, x, skip, acts, z, dpre, bufA, bufB, bufC, bufD, total;
+};
+static WsLayout ws_layout(const ovc_ctx* c, int B, int Tmax) {
+  WsLayout L;
+  L.P = (int)round_up((size_t)Tmax, 4);
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = round_up(o + n, 64); return r; };
+  L.cond = take((size_t)B * c->cond_rows_out);
+  L.x = take((size_t)B * 192 * L.P);
+  L.skip = take((size_t)B * 192 * L.P);
+  L.acts = take((size_t)B * 192 * L.P);
+  L.z = take((size_t)B * 192 * L.P);
+  L.dpre = take((size_t)B * 512 * L.P);
+  const size_t big = (size_t)B * 8192 * L.P;
+  L.bufA = take(big);
+  L.bufB = take(big);
+  L.bufC = take(big);
+  L.bufD = take(big);
+  L.total = o;
+  return L;
+}
+
+struct Run {
+  ovc_ctx* c;
+  cudaStream_t st;
+  int B, Tmax, P;
+  const long long* lens;
+  const long long* glens;   // generator lengths: lens when ragged, NULL (= Tmax) otherwise
+  double sum_len;           // sum over batch of generator frames (for FLOP/byte accounting): B*Tmax upper bound
+};
+
+static int launch(Run& r, const ConvLayer& L, ConvArgs a, int t_len, bool profiled = false, double flops = 0,
+                  double bytes = 0) {
+  a.w = r.c->d_w + L.w_off;
+  a.n_chunks = L.n_chunks;
+  a.cin = L.cin;
+  a.tmax = r.Tmax;
+  if (a.div == 0.f) a.div = 1.f;
+  ovc_ctx* c = r.c;
+  const bool prof = profiled && c->prof;
+  if (prof) {
+    if (c->ev_used + 2 > c->ev.size()) {
+      const size_t old = c->ev.size();
+      c->ev.resize(old + 256);
+      for (size_t i = old; i < c->ev.size(); ++i) CK(cudaEventCreate(&c->ev[i]));
+    }
+    CK(cudaEventRecord(c->ev[c->ev_used], r.st));
+  }
+  CK(kLaunch[L.variant](a, t_len, L.row_tiles, r.B, r.st));
+  c->launches++;
+  if (prof) {
+    CK(cudaEventRecord(c->ev[c->ev_used + 1], r.st));
+    c->ev_used += 2;
+    c->ev_flops.push_back(flops);
+    c->ev_bytes.push_back(bytes);
+  }
+  return OVC_OK;
+}
+
+static int tap(Run& r, const char* name, const float* src, int C, int T, int pitch) {
+  ovc_ctx* c = r.c;
+  if (!c->debug) return OVC_OK;
+  DebugBuf& d = c->taps[name];
+  const size_t n = (size_t)r.B * C * pitch;
+  if (d.floats < n) {
+    if (d.d) cudaFree(d.d);
+    CK(cudaMalloc(&d.d, n * sizeof(float)));
+    d.floats = n;
+  }
+  d.shape[0] = r.B; d.shape[1] = C; d.shape[2] = T; d.shape[3] = pitch;
+  CK(cudaMemcpyAsync(d.d, src, n * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
+  return OVC_OK;
+}
+
+#define TRY(expr)                   \
+  do {                              \
+    int rc_ = (expr);               \
+    if (rc_ != OVC_OK) return rc_;  \
+  } while (0)
+
+// one WN stack (modules.py:185-210): x <- in place, skip <- output
+static int run_wn(Run& r, const WNLayers& wn, float* x, float* skip, float* acts, const float* cond, int cond_bs) {
+  const int P = r.P, T = r.Tmax;
+  const long long bs = 192LL * P;
+  const int n = (int)wn.in.size();
+  for (int i = 0; i < n; ++i) {
+    ConvArgs a{};
+    a.x = x; a.x_bs = bs; a.x_pitch = P;
+    a.bias = cond + (size_t)i * 384; a.bias_bs = cond_bs;
+    a.y = acts; a.y_bs = bs; a.y_pitch = P;
+    a.lens_in = r.lens; a.lens_out = r.lens; a.mul_in = 1; a.mul_out = 1;
+    a.slope = 1.f;
+    TRY(launch(r, wn.in[i], a, T));
+    ConvArgs b{};
+    b.x = acts; b.x_bs = bs; b.x_pitch = P;
+    b.bias = r.c->d_w + wn.rs[i].b_off; b.bias_bs = 0;
+    b.y = x; b.y_bs = bs; b.y_pitch = P;
+    b.s = skip; b.s_bs = bs; b.s_pitch = P;
+    b.lens_in = r.lens; b.lens_out = r.lens; b.mul_in = 1; b.mul_out = 1;
+    b.slope = 1.f;
+    b.split = (i < n - 1) ? 192 : 0;
+    b.flags = (i == 0) ? F_FIRST : 0;
+    TRY(launch(r, wn.rs[i], b, T));
+  }
+  return OVC_OK;
+}
+
+static int run_flow(Run& r, const WsLayout& W, float* ws, bool reverse, const float* cond_all) {
+  ovc_ctx* c = r.c;
+  const int P = r.P, T = r.Tmax;
+  const long long bs = 192LL * P;
+  float* z = ws + W.z;
+  float* x = ws + W.x;
+  float* skip = ws + W.skip;
+  float* acts = ws + W.acts;
+  const int sect = reverse ? c->cond_off_ftgt : c->cond_off_fsrc;
+  for (int step = 0; step < 4; ++step) {
+    const int f = reverse ? 3 - step : step;
+    const bool flipped = f & 1;
+    // pre: x0 (physical lower half, or upper half when flipped) -> h     (modules.py:438-439)
+    ConvArgs a{};
+    a.x = z + (flipped ? 96 * (size_t)P : 0); a.x_bs = bs; a.x_pitch = P;
+    a.bias = c->d_w + c->flow_pre[f].b_off; a.bias_bs = 0;
+    a.y = x; a.y_bs = bs; a.y_pitch = P;
+    a.lens_in = r.lens; a.lens_out = r.lens; a.mul_in = 1; a.mul_out = 1;
+    a.slope = 1.f; a.div = 1.f;
+    TRY(launch(r, c->flow_pre[f], a, T));
+    TRY(run_wn(r, c->flow_wn[f], x, skip, acts, cond_all + sect + f * 4 * 384, c->cond_rows_out));
+    // post + coupling update of x1 in place                                (modules.py:441-454)
+    ConvArgs b{};
+    b.x = skip; b.x_bs = bs; b.x_pitch = P;
+    b.bias = c->d_w + c->flow_post[f].b_off; b.bias_bs = 0;
+    b.y = z + (flipped ? 0 : 96 * (size_t)P); b.y_bs = bs; b.y_pitch = P;
+    b.lens_in = r.lens; b.lens_out = r.lens; b.mul_in = 1; b.mul_out = 1;
+    b.slope = 1.f;
+    b.sign = reverse ? -1.f : 1.f;
+    TRY(launch(r, c->flow_post[f], b, T));
+  }
+  return OVC_OK;
+}
+
+static int run_vc(ovc_ctx* c, const float* spec, const long long* lens, const float* g_src, const float* g_tgt,
+                  const float* noise, uint64_t seed, float tau, int B, int Tmax, int ragged, float* o_hat,
+                  float* z_out, float* zp_out, float* zh_out, cudaStream_t st) {
+  const WsLayout W = ws_layout(c, B, Tmax);
+  if (W.total > c->ws_floats) {
+    CK(cudaStreamSynchronize(st));
+    if (c->d_ws) CK(cudaFree(c->d_ws));
+    c->d_ws = nullptr;
+    c->ws_floats = 0;
+    cudaError_t e = cudaMalloc(&c->d_ws, W.total * sizeof(float));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(OVC_ERR_NOMEM, "workspace of %.2f GB for B=%d Tmax=%d does not fit: %s", W.total * 4e-9, B, Tmax,
+                  cudaGetErrorString(e));
+    }
+    c->ws_floats = W.total;
+  }
+  float* ws = c->d_ws;
+  Run r{c, st, B, Tmax, W.P, lens, ragged ? lens : nullptr, (double)B * Tmax};
+  c->launches = 0;
+  const int P = W.P;
+  const long long bs192 = 192LL * P;
+
+  // ---- every speaker-conditioning 1x1 conv in one launch
+  {
+    CondArgs a;
+    a.w = c->d_w + c->cond_w_off; a.bias = c->d_w + c->cond_b_off;
+    a.w_row = c->d_cond_wrow; a.sel = c->d_cond_sel;
+    a.g_src = g_src; a.g_tgt = g_tgt; a.out = ws + W.cond;
+    a.rows_out = c->cond_rows_out; a.gin = c->hp.gin_channels;
+    dim3 grid((c->cond_rows_out + 7) / 8, B);
+    cond_kernel<<<grid, 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  const float* cond = ws + W.cond;
+  TRY(tap(r, "cond", cond, 1, c->cond_rows_out, c->cond_rows_out));
+
+  // ---- posterior encoder (models.py:212-221)
+  {
+    ConvArgs a{};
+    a.x = spec; a.x_bs = (long long)c->hp.spec_channels * Tmax; a.x_pitch = Tmax;
+    a.bias = c->d_w + c->enc_pre.b_off; a.bias_bs = 0;
+    a.y = ws + W.x; a.y_bs = bs192; a.y_pitch = P;
+    a.lens_in = lens; a.lens_out = lens; a.mul_in = 1; a.mul_out = 1;
+    a.slope = 1.f; a.div = 1.f;
+    TRY(launch(r, c->enc_pre, a, Tmax));
+    TRY(tap(r, "enc.pre", ws + W.x, 192, Tmax, P));
+    TRY(run_wn(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, cond + c->cond_off_enc, c->cond_rows_out));
+    TRY(tap(r, "enc.wn", ws + W.skip, 192, Tmax, P));
+    ConvArgs p{};
+    p.x = ws + W.skip; p.x_bs = bs192; p.x_pitch = P;
+    p.bias = c->d_w + c->enc_proj.b_off; p.bias_bs = 0;
+    p.y = ws + W.z; p.y_bs = bs192; p.y_pitch = P;
+    p.r = noise; p.r_bs = 192LL * Tmax; p.r_pitch = Tmax;
+    p.lens_in = lens; p.lens_out = lens; p.mul_in = 1; p.mul_out = 1;
+    p.slope = 1.f; p.tau = tau; p.seed = seed;
+    TRY(launch(r, c->enc_proj, p, Tmax));
+  }
+  auto copy_latent = [&](float* dst) -> int {
+    if (!dst) return OVC_OK;
+    dim3 grid((Tmax + 255) / 256, 192, B);
+    copy_latent_kernel<<<grid, 256, 0, st>>>(ws + W.z, P, dst, Tmax, 192, lens);
+    CK(cudaGetLastError());
+    c->launches++;
+    return OVC_OK;
+  };
+  TRY(copy_latent(z_out));
+  // ---- flow forward with g_src, reverse with g_tgt (models.py:496-497)
+  TRY(run_flow(r, W, ws, false, cond));
+  TRY(copy_latent(zp_out));
+  TRY(run_flow(r, W, ws, true, cond));
+  TRY(copy_latent(zh_out));
+
+  // ---- generator (models.py:272-291).  Lengths: frames * cumulative upsampling.
+  {
+    ConvArgs a{};
+    a.x = ws + W.z; a.x_bs = bs192; a.x_pitch = P;
+    a.bias = cond + c->cond_off_dec; a.bias_bs = c->cond_rows_out;
+    a.y = ws + W.dpre; a.y_bs = 512LL * P; a.y_pitch = P;
+    a.lens_in = lens;          // z_hat * y_mask
+    a.lens_out = r.glens; a.mul_in = 1; a.mul_out = 1;
+    a.slope = 1.f; a.div = 1.f;
+    TRY(launch(r, c->dec_pre, a, Tmax));
+    TRY(tap(r, "dec.pre", ws + W.dpre, 512, Tmax, P));
+  }
+  float* bufA = ws + W.bufA; float* bufB = ws + W.bufB; float* bufC = ws + W.bufC; float* bufD = ws + W.bufD;
+  const float* stage_in = ws + W.dpre;
+  int cin = 512, up = 1;
+  for (int i = 0; i < 4; ++i) {
+    const int s = c->hp.upsample_rates[i];
+    const int cout = cin / 2;
+    const int up_out = up * s;
+    const int pitch_in = P * up, pitch_out = P * up_out;
+    // leaky_relu(0.1) + ConvTranspose1d (models.py:278-279), polyphase
+    {
+      ConvArgs a{};
+      a.x = stage_in; a.x_bs = (long long)cin * pitch_in; a.x_pitch = pitch_in;
+      a.bias = c->d_w + c->dec_ups[i].b_off; a.bias_bs = 0;
+      a.y = bufA; a.y_bs = (long long)cout * pitch_out; a.y_pitch = pitch_out;
+      a.lens_in = r.glens; a.lens_out = r.glens; a.mul_in = up; a.mul_out = up;   // kernel time axis = input samples
+      a.slope = 0.1f;
+      TRY(launch(r, c->dec_ups[i], a, Tmax * up));
+      char nm[32]; snprintf(nm, sizeof nm, "dec.ups%d", i);
+      TRY(tap(r, nm, bufA, cout, Tmax * up_out, pitch_out));
+    }
+    // MRF: xs = sum_j ResBlock1_j(x) / 3 (models.py:280-286; ResBlock1 = modules.py:296-309)
+    const long long bsC = (long long)cout * pitch_out;
+    const int Tlen = Tmax * up_out;
+    for (int j = 0; j < 3; ++j) {
+      const int K = c->hp.resblock_kernel_sizes[j];
+      for (int d = 0; d < 3; ++d) {
+        const double fl = 2.0 * cout * cout * K * r.sum_len * up_out;
+        const double by = 2.0 * cout * r.sum_len * up_out * 4.0;
+        const float* xin = d == 0 ? bufA : bufB;
+        ConvArgs a{};
+        a.x = xin; a.x_bs = bsC; a.x_pitch = pitch_out;
+        a.bias = c->d_w + c->rb_c1[i * 3 + j][d].b_off; a.bias_bs = 0;
+        a.y = bufC; a.y_bs = bsC; a.y_pitch = pitch_out;
+        a.lens_in = r.glens; a.lens_out = r.glens; a.mul_in = up_out; a.mul_out = up_out;
+        a.slope = 0.1f; a.div = 1.f;
+        TRY(launch(r, c->rb_c1[i * 3 + j][d], a, Tlen, true, fl, by));
+        ConvArgs b{};
+        b.x = bufC; b.x_bs = bsC; b.x_pitch = pitch_out;
+        b.bias = c->d_w + c->rb_c2[i * 3 + j][d].b_off; b.bias_bs = 0;
+        b.r = xin; b.r_bs = bsC; b.r_pitch = pitch_out;
+        b.lens_in = r.glens; b.lens_out = r.glens; b.mul_in = up_out; b.mul_out = up_out;
+        b.slope = 0.1f; b.div = 1.f;
+        if (d < 2) {
+          b.y = bufB; b.y_bs = bsC; b.y_pitch = pitch_out;
+        } else {
+          b.y = bufD; b.y_bs = bsC; b.y_pitch = pitch_out;
+          if (j > 0) b.flags = F_ACCUM;
+          if (j == 2) b.div = 3.f;
+        }
+        TRY(launch(r, c->rb_c2[i * 3 + j][d], b, Tlen, true, fl, by));
+      }
+    }
+    char nm[32]; snprintf(nm, sizeof nm, "dec.stage%d", i);
+    TRY(tap(r, nm, bufD, cout, Tlen, pitch_out));
+    stage_in = bufD;
+    cin = cout; up = up_out;
+  }
+  // leaky_relu(0.01) + conv_post + tanh (models.py:287-289)
+  {
+    const int y_len = Tmax * up;   // 256 * Tmax
+    dim3 grid((y_len / 4 + 255) / 256, B);
+    conv_post_kernel<32><<<grid, 256, 0, st>>>(bufD, 32LL * P * up, P * up, c->d_w + c->post_w_off, o_hat,
+                                              (long long)y_len, y_len, r.glens, Tmax, up);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  return OVC_OK;
+}
+
+}  // namespace ovc
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int ovc_abi_version(void) { return OVC_ABI_VERSION; }
+
+const char* ovc_last_error(void) { return ovc::g_err.c_str(); }
+
+int ovc_create(const ovc_hparams* hp, int device, ovc_ctx** out) {
+  if (!hp || !out) return fail(OVC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = validate_hparams(hp);
+  if (rc != OVC_OK) return rc;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(OVC_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return fail(OVC_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(OVC_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+  ovc_ctx* c = new ovc_ctx();
+  c->hp = *hp;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return OVC_OK;
+}
+
+void ovc_destroy(ovc_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->d_w) cudaFree(c->d_w);
+  if (c->d_ws) cudaFree(c->d_ws);
+  if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
+  if (c->d_cond_sel) cudaFree(c->d_cond_sel);
+  for (auto& e : c->ev) cudaEventDestroy(e);
+  for (auto& kv : c->taps)
+    if (kv.second.d) cudaFree(kv.second.d);
+  delete c;
+}
+
+int ovc_load_tensor(ovc_ctx* c, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!c || !key || !data || !shape || ndim < 1 || ndim > 4) return fail(OVC_ERR_INVALID, "bad argument to ovc_load_tensor");
+  const std::string k(key);
+  if (!key_is_hot(k)) return 1;
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  if (n <= 0) return fail(OVC_ERR_INVALID, "tensor '%s' is empty", key);
+  t.data.assign(data, data + n);
+  c->sd[k] = std::move(t);
+  c->finalized = false;
+  return OVC_OK;
+}
+
+int ovc_finalize_weights(ovc_ctx* c) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  return finalize(c);
+}
+
+size_t ovc_workspace_floats(const ovc_ctx* c, int B, int Tmax) {
+  if (!c || B < 1 || Tmax < 1 || !c->finalized) return 0;
+  return ws_layout(c, B, Tmax).total;
+}
+
+int ovc_voice_conversion(ovc_ctx* c, const float* spec, const int64_t* lengths, const float* g_src, const float* g_tgt,
+                         const float* noise, uint64_t seed, float tau, int B, int Tmax, int ragged, float* o_hat, float* z,
+                         float* z_p, float* z_hat, void* stream) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  if (!c->finalized) return fail(OVC_ERR_STATE, "ovc_finalize_weights has not been called");
+  if (!spec || !lengths || !g_src || !g_tgt || !o_hat) return fail(OVC_ERR_INVALID, "null tensor argument");
+  if (B < 1 || Tmax < 1) return fail(OVC_ERR_INVALID, "B and Tmax must be positive (got %d, %d)", B, Tmax);
+  if ((long long)Tmax * 256 * 64 > 2000000000LL) return fail(OVC_ERR_INVALID, "Tmax %d too large for 32-bit indexing", Tmax);
+  if (B > 65535) return fail(OVC_ERR_INVALID, "B %d exceeds the grid limit", B);
+  CK(cudaSetDevice(c->device));
+  c->ev_used = c->prof ? c->ev_used : 0;
+  return run_vc(c, spec, (const long long*)lengths, g_src, g_tgt, noise, seed, tau, B, Tmax, ragged, o_hat, z, z_p, z_hat,
+                (cudaStream_t)stream);
+}
+
+int ovc_last_launch_count(const ovc_ctx* c) { return c ? c->launches : 0; }
+
+int ovc_profile_enable(ovc_ctx* c, int enable) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  c->prof = enable != 0;
+  c->ev_used = 0;
+  c->ev_flops.clear();
+  c->ev_bytes.clear();
+  return OVC_OK;
+}
+
+int ovc_profile_read(ovc_ctx* c, double* ms, int64_t* launches, double* flops, double* bytes) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  double tms = 0, tf = 0, tb = 0;
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    float m = 0;
+    CK(cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]));
+    tms += m;
+    tf += c->ev_flops[i / 2];
+    tb += c->ev_bytes[i / 2];
+  }
+  if (ms) *ms = tms;
+  if (launches) *launches = (int64_t)(c->ev_used / 2);
+  if (flops) *flops = tf;
+  if (bytes) *bytes = tb;
+  c->ev_used = 0;
+  c->ev_flops.clear();
+  c->ev_bytes.clear();
+  return OVC_OK;
+}
+
+int ovc_debug_enable(ovc_ctx* c, int enable) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  c->debug = enable != 0;
+  return OVC_OK;
+}
+
+int ovc_debug_fetch(ovc_ctx* c, const char* name, float* host_out, size_t max_floats, int64_t* shape4) {
+  if (!c || !name) return fail(OVC_ERR_INVALID, "null argument");
+  auto it = c->taps.find(name);
+  if (it == c->taps.end()) return fail(OVC_ERR_INVALID, "no debug tap named '%s' (enable debug and run a call first)", name);
+  const DebugBuf& d = it->second;
+  const size_t n = (size_t)d.shape[0] * d.shape[1] * d.shape[3];
+  if (shape4) memcpy(shape4, d.shape, sizeof d.shape);
+  if (host_out) {
+    if (max_floats < n) return fail(OVC_ERR_INVALID, "buffer too small for tap '%s': need %zu floats", name, n);
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_out, d.d, n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return OVC_OK;
+}
+
+}  // extern "C"
