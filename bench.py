@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds per second of ToneColorConverter.convert on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 32] [--secs 10] [--impl native|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic utterances.  The default
+workload is BASELINE.json configs[1]: batch 32 x 10 s clips at 22.05 kHz on one B200 (fp32
+arithmetic -- stricter than the config's "fp16").  For N > 1 launch under torchrun: one rank per
+GPU, every rank converts its own `batch` clips (weak scaling, no data-path collective; NCCL only
+broadcasts the checkpoint and, in the end-to-end leg, gathers the output waveforms on rank 0).
+
+One JSON line on stdout (rank 0):
+  value      device-resident: waveforms already in HBM -> spectrogram -> voice_conversion, CUDA events
+  e2e        through ToneColorConverter.convert_batch with HOST numpy waveforms: pinned H2D, STFT,
+             voice_conversion, D2H of the samples, all inside the timed region
+  roofline   generator ResBlock conv family (90 % of the FLOPs): algorithmic layer-granular bytes
+             / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs, plus the fp32 FFMA numbers that
+             actually bind
+  cpu_baseline  the oracle port of the reference's CPU path on this box's host cores (N=1 only)
+--impl reference times that CPU path alone (the reference arm).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 22050
+HOP = 256
+GFLOP_PER_FRAME = 0.65766          # 657.66 MFLOP per spectrogram frame
+FFMA_PEAK_TFLOPS = 74.4            # nominal 148 SM x 128 lanes x 2 x 1.965 GHz
+
+
+def synth_wave(i, secs):
+    rng = np.random.default_rng(1000 + i)
+    L = int(round(secs * SR))
+    return (0.5 * (2.0 * rng.random(L, dtype=np.float32) - 1.0)).astype(np.float32)
+
+
+def synth_se(i, base):
+    import torch
+    return 0.1 * torch.randn(1, 256, 1, generator=torch.Generator().manual_seed(base + i))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(suffix=".csv")
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 7:
+                    continue
+                sm.append(float(p[0]))
+                mx = float(p[1])
+                for n, v in zip(names, p[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_throughput(n_clips, secs, threads=None):
+    """Time the oracle port of the reference's convert() arithmetic (spectrogram + voice_conversion,
+    batch 1 per utterance like openvoice/api.py:141-155) on the host cores."""
+    import torch
+    from oracle import vc_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = O.synthetic_state_dict(1234)
+    waves = [torch.from_numpy(synth_wave(i, secs)) for i in range(n_clips)]
+    with torch.no_grad():
+        O.convert_waveform(sd, waves[0][: SR], synth_se(0, 2000), synth_se(0, 3000), None, 0.3)   # warm-up
+        t0 = time.perf_counter()
+        for i, w in enumerate(waves):
+            T = w.shape[0] // HOP
+            noise = torch.randn(1, 192, T)
+            O.convert_waveform(sd, w, synth_se(i, 2000), synth_se(i, 3000), noise, 0.3)
+        dt = time.perf_counter() - t0
+    audio_s = sum((w.shape[0] // HOP) * HOP for w in waves) / SR
+    return audio_s / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_clips = max(1, min(args.batch, args.ref_clips))
+    times = []
+    val = None
+    for s in range(args.warmup + args.steps):
+        v, dt, threads = cpu_reference_throughput(n_clips, args.secs)
+        if s >= args.warmup:
+            times.append(dt)
+            val = (n_clips * (int(round(args.secs * SR)) // HOP) * HOP / SR) / float(np.mean(times))
+    sample = f"{n_clips} x {args.secs:g} s clips per step, batch 1 each (convert semantics), fp32, torch CPU ({threads} threads)"
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ToneColorConverter.convert, {args.secs:g} s clips @ {SR} Hz (bounded sample of the batch-{args.batch} workload)",
+                   "batch": n_clips, "secs": args.secs},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--secs", type=float, default=10.0)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU reference arm")
+    ap.add_argument("--cpu-clips", type=int, default=8, help="clips in the cpu_baseline sample of the native arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from oracle import vc_oracle as O          # synthetic checkpoint recipe + cpu_baseline only
+    from openvoice_b200.api import ToneColorConverter
+    from openvoice_b200.mel_processing import spectrogram_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun"
+
+    # ---- model: rank 0 owns the checkpoint, NCCL broadcasts it (north_star)
+    schema = O.state_dict_schema()
+    names = sorted(schema)
+    sizes = [int(np.prod(schema[k])) for k in names]
+    if rank == 0:
+        sd = O.synthetic_state_dict(1234)
+        flat = torch.cat([sd[k].reshape(-1) for k in names]).to(dev)
+    else:
+        flat = torch.empty(sum(sizes), device=dev)
+    if world > 1:
+        dist.broadcast(flat, 0)
+    parts = torch.split(flat.cpu(), sizes)
+    sd = {k: p.reshape(schema[k]) for k, p in zip(names, parts)}
+    del flat
+    with tempfile.TemporaryDirectory() as td:
+        cfg = os.path.join(td, "config.json")
+        json.dump(O.DEFAULT_HPARAMS, open(cfg, "w"))
+        conv = ToneColorConverter(cfg, device=dev, enable_watermark=False)
+    conv.model.load_state_dict(sd)
+    del sd
+
+    B, secs = args.batch, args.secs
+    waves = [synth_wave(rank * B + i, secs) for i in range(B)]
+    L = len(waves[0])
+    T = L // HOP
+    audio_s_step = B * T * HOP / SR
+    src = torch.cat([synth_se(rank * B + i, 2000) for i in range(B)]).to(dev)
+    tgt = torch.cat([synth_se(rank * B + i, 3000) for i in range(B)]).to(dev)
+    wav_dev = torch.from_numpy(np.stack(waves)).to(dev)
+    lengths = torch.full((B,), T, dtype=torch.int64, device=dev)
+    hp = conv.hps.data
+
+    def device_step(seed):
+        spec = spectrogram_torch(wav_dev, hp.filter_length, hp.sampling_rate, hp.hop_length, hp.win_length).contiguous()
+        o, _, _ = conv.model.voice_conversion(spec, lengths, src, tgt, tau=0.3, seed=seed, ragged=True, latents=False)
+        return o
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg
+    for s in range(args.warmup):
+        device_step(s)
+    native = conv.model.native
+    native.profile_enable(True)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        device_step(1000 + s)
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    prof = native.profile_read()
+    native.profile_enable(False)
+    launches_per_call = native.last_launch_count
+
+    # ---- end-to-end leg: host numpy in, host numpy out, through the public API
+    def e2e_step():
+        res = conv.convert_batch(waves, src, tgt, tau=0.3, max_batch=B)
+        if world > 1:   # gather the waveforms on rank 0 over NCCL
+            mine = torch.from_numpy(np.stack(res)).to(dev)
+            bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+            dist.gather(mine, bucket, dst=0)
+        return res
+
+    for s in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for s in range(args.steps):
+        res = e2e_step()
+    g1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max_over_ranks(max(g0.elapsed_time(g1), wall_ms)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    assert res[0].shape[0] == T * HOP and np.isfinite(res[0]).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    k_ms = prof["ms"] / max(1, prof["launches"])
+    ach_gbs = prof["bytes"] / max(1e-9, prof["ms"] * 1e-3) / 1e9
+    ach_tf = prof["flops"] / max(1e-9, prof["ms"] * 1e-3) / 1e12
+    roofline = {
+        "kernel": "conv1d_f32<EPI_LINEAR> (generator ResBlock1 convs, 72 launches per call)",
+        "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+        "traffic": None, "peak_source": peak_src,
+        "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_dev,
+        "binding": "fp32 FFMA (dense contraction, SURVEY.md section 8d)",
+        "ffma": {"achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FFMA_PEAK_TFLOPS,
+                 "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"},
+    }
+    value = world * audio_s_step / (ms_dev * 1e-3)
+    e2e_val = world * audio_s_step / (ms_e2e * 1e-3)
+    line = {
+        "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ToneColorConverter.convert_batch, batch {B} x {secs:g} s clips @ {SR} Hz per GPU "
+                               "(BASELINE configs[1]), seeded synthetic checkpoint, tau 0.3, in-kernel Philox noise",
+                   "batch_per_gpu": B, "global_batch": B * world, "secs": secs, "frames": T,
+                   "l2": "activations per step (>3 GB) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": f"replicas x{world}"},
+        "tflops_algorithmic": world * B * T * GFLOP_PER_FRAME / ms_dev,
+        "e2e": {"value": e2e_val, "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(B * L * 4 + B * 8), "d2h_bytes_per_step": int(B * T * HOP * 4)},
+        "gpu_launches": int(launches_per_call * args.steps * 2),
+        "launches_per_call": int(launches_per_call),
+        "roofline": roofline, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, threads = cpu_reference_throughput(args.cpu_clips, secs)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_clips} x {secs:g} s clips, batch 1 each, fp32 torch CPU, {dt:.1f} s"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
