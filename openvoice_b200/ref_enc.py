@@ -42,6 +42,10 @@ class ReferenceEncoder:
     def __call__(self, inputs, mask=None):
         if self.p is None:
             raise RuntimeError("ref_enc.* weights were not in the checkpoint")
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):   # fp32 like the reference on CPU
+            return self._forward(inputs)
+
+    def _forward(self, inputs):
         p = self.p
         N = inputs.size(0)
         x = inputs.reshape(N, 1, -1, self.spec_channels)
