@@ -1,0 +1,110 @@
+"""Multi-GPU driver for the converter: replicas only.
+
+Utterances are independent, so N GPUs = N replicas of the model, one process per GPU
+(``torchrun``), no collective inside the hot path.  ``torch.distributed`` (NCCL over NVLink on
+GPUs, gloo in the CPU tests) is used for exactly two things, as north_star prescribes:
+broadcasting the checkpoint from rank 0 and gathering the output waveforms on rank 0.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def lpt_shard(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Longest-processing-time-first assignment of items (cost = samples) to ``world`` ranks.
+    Deterministic; every rank computes the same table.  Returns per-rank index lists."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * world
+    shards: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda q: (loads[q], q))
+        shards[r].append(i)
+        loads[r] += costs[i]
+    return shards
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def broadcast_state_dict(sd: Optional[Dict[str, torch.Tensor]], device: str = "cpu", src: int = 0) -> Dict[str, torch.Tensor]:
+    """Rank ``src`` passes the checkpoint's state dict, the others pass None; everybody returns the
+    same dict (CPU fp32 tensors).  One metadata broadcast + one flat tensor broadcast (~128 MB)."""
+    rank, world = _world()
+    if world == 1:
+        assert sd is not None
+        return sd
+    meta = [None]
+    if rank == src:
+        names = sorted(sd)
+        meta = [[(k, tuple(sd[k].shape)) for k in names]]
+    dist.broadcast_object_list(meta, src=src)
+    layout = meta[0]
+    sizes = [int(np.prod(s)) if len(s) else 1 for _, s in layout]
+    if rank == src:
+        flat = torch.cat([sd[k].detach().float().reshape(-1) for k, _ in layout]).to(device)
+    else:
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+    dist.broadcast(flat, src=src)
+    flat = flat.cpu()
+    out, o = {}, 0
+    for (k, shape), n in zip(layout, sizes):
+        out[k] = flat[o: o + n].reshape(shape).clone()
+        o += n
+    return out
+
+
+def gather_waveforms(local: List[np.ndarray], local_idx: List[int], n_total: int, device: str = "cpu",
+                     dst: int = 0) -> Optional[List[np.ndarray]]:
+    """Gather variable-length float32 waveforms on rank ``dst`` in the original item order.
+    Two fixed-shape collectives: lengths/indices table, then a padded [n_max, L_max] block."""
+    rank, world = _world()
+    if world == 1:
+        out: List[Optional[np.ndarray]] = [None] * n_total
+        for i, a in zip(local_idx, local):
+            out[i] = a
+        return out  # type: ignore[return-value]
+    n_loc = len(local)
+    stats = torch.tensor([n_loc, max([len(a) for a in local], default=0)], dtype=torch.int64, device=device)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    n_max, l_max = int(stats[0]), int(stats[1])
+    table = torch.full((n_max, 2), -1, dtype=torch.int64, device=device)
+    block = torch.zeros((n_max, max(l_max, 1)), dtype=torch.float32, device=device)
+    for j, (i, a) in enumerate(zip(local_idx, local)):
+        table[j, 0], table[j, 1] = i, len(a)
+        block[j, : len(a)] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+    tables = [torch.empty_like(table) for _ in range(world)] if rank == dst else None
+    blocks = [torch.empty_like(block) for _ in range(world)] if rank == dst else None
+    dist.gather(table, tables, dst=dst)
+    dist.gather(block, blocks, dst=dst)
+    if rank != dst:
+        return None
+    out = [None] * n_total
+    for t, b in zip(tables, blocks):
+        t, b = t.cpu(), b.cpu()
+        for j in range(n_max):
+            i, n = int(t[j, 0]), int(t[j, 1])
+            if i >= 0:
+                out[i] = b[j, :n].numpy().copy()
+    assert all(o is not None for o in out)
+    return out  # type: ignore[return-value]
+
+
+def convert_sharded(convert_fn: Callable[..., List[np.ndarray]], audios: Sequence[np.ndarray], src_se, tgt_se,
+                    device: str = "cpu", **kw) -> Optional[List[np.ndarray]]:
+    """Every rank holds the same utterance list; each converts its LPT shard with ``convert_fn``
+    (normally ``ToneColorConverter.convert_batch``) and rank 0 receives all results in order.
+    ``src_se`` / ``tgt_se``: one embedding for all items, or a per-item sequence."""
+    rank, world = _world()
+    shards = lpt_shard([len(a) for a in audios], world)
+    mine = shards[rank]
+    pick = (lambda se: [se[i] for i in mine]) if isinstance(src_se, (list, tuple)) else (lambda se: se)
+    res = convert_fn([audios[i] for i in mine], pick(src_se),
+                     [tgt_se[i] for i in mine] if isinstance(tgt_se, (list, tuple)) else tgt_se, **kw) if mine else []
+    return gather_waveforms(res, mine, len(audios), device=device)

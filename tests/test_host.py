@@ -1,0 +1,174 @@
+"""CPU-side tests: the C ABI library loads and exports what include/ovc.h declares, hparams
+marshalling / validation, loud failure without a GPU, config + audio helpers, and the multi-GPU
+driver logic under gloo (world_size 2)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "ovc.h")).read()
+    return sorted(set(re.findall(r"OVC_API\s+[\w\s\*]+?\b(ovc_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from openvoice_b200 import _native
+    lib = _native.load_library()
+    declared = header_functions()
+    assert len(declared) >= 13
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ovc.h but not exported"
+    assert sorted(_native.EXPORTS) == declared
+    assert lib.ovc_abi_version() == _native.ABI_VERSION
+
+
+def test_library_contains_sm100a_tma_code():
+    """The shipped cubin is sm_100a and stages weights with TMA bulk copies (UBLKCP)."""
+    lib = os.path.join(ROOT, "openvoice_b200", "libovc_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["bash", "-c", f"cuobjdump -sass -fun '_ZN3ovc10conv1d_f32INS_7ConvCfgILi1ELi1ELi2ELi2ELi8ELi2ELi1ELi16EEEEEvNS_8ConvArgsE' {lib} | grep -c -E 'UBLKCP|SYNCS'"],
+                          capture_output=True, text=True).stdout.strip()
+    assert int(sass or 0) > 0
+
+
+def test_hparams_marshalling(hps):
+    from openvoice_b200 import _native
+    s = _native.hparams_struct(hps)
+    assert (s.spec_channels, s.inter_channels, s.hidden_channels, s.gin_channels) == (513, 192, 192, 256)
+    assert list(s.resblock_kernel_sizes)[:3] == [3, 7, 11] and list(s.upsample_rates) == [8, 8, 2, 2]
+    assert [list(r) for r in s.resblock_dilations][:3] == [[1, 3, 5]] * 3
+    assert s.zero_g == 0 and s.hop_length == 256 and s.resblock == 1
+
+
+def test_create_fails_loudly_without_gpu_and_on_bad_hparams(hps):
+    """No CPU fallback: without a device ovc_create errors; unsupported hparams are refused."""
+    from openvoice_b200 import _native
+    lib = _native.load_library()
+    bad = _native.hparams_struct(hps)
+    bad.hidden_channels = 128
+    h = C.c_void_p()
+    assert lib.ovc_create(C.byref(bad), 0, C.byref(h)) == -1
+    assert b"192" in lib.ovc_last_error()
+    bad = _native.hparams_struct(hps)
+    bad.upsample_rates[0] = 4
+    assert lib.ovc_create(C.byref(bad), 0, C.byref(h)) == -1
+    if not torch.cuda.is_available():
+        with pytest.raises(_native.OvcError, match="no CUDA device"):
+            _native.NativeConverter(hps, 0)
+        from openvoice_b200.api import NativeSynthesizer
+        with pytest.raises(RuntimeError):
+            NativeSynthesizer(hps, "cpu")
+    assert lib.ovc_voice_conversion(None, None, None, None, None, None, 0, 0.3, 1, 1, 0, None, None, None, None, None) < 0
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    from openvoice_b200 import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setenv("OVC_B200_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(_native.OvcError, match="no CPU"):
+        _native.load_library()
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "openvoice_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("vc_oracle", "oracle") or f == "x", f
+    txt = open(os.path.join(ROOT, "openvoice_b200", "api.py")).read()
+    assert "import oracle" not in txt and "from oracle" not in txt
+
+
+def test_hparams_loader_and_bit_codec(tmp_path):
+    from openvoice_b200 import utils
+    from oracle import vc_oracle as O
+    p = tmp_path / "config.json"
+    hp = dict(O.DEFAULT_HPARAMS, _version_="v2")
+    p.write_text(json.dumps(hp))
+    h = utils.get_hparams_from_file(str(p))
+    assert h.data.sampling_rate == 22050 and h["model"]["upsample_rates"] == [8, 8, 2, 2]
+    assert "model" in h and len(h) == 3 and getattr(h, "_version_") == "v2"
+    bits = utils.string_to_bits("@MyShell")
+    assert bits.shape == (8, 8) and utils.bits_to_string(bits) == "@MyShell"
+    assert utils.bits_to_string(utils.string_to_bits("ab")) == "ab" + " " * 6   # space padded (utils.py:57)
+
+
+def test_audio_loader(tmp_path):
+    from scipy.io import wavfile
+    from openvoice_b200.api import _load_audio, _write_audio
+    x = (0.3 * np.sin(np.arange(22050) * 0.05)).astype(np.float32)
+    np.save(tmp_path / "a.npy", x)
+    assert np.array_equal(_load_audio(str(tmp_path / "a.npy"), 22050), x)
+    wavfile.write(tmp_path / "a.wav", 22050, (x * 32767).astype(np.int16))
+    y = _load_audio(str(tmp_path / "a.wav"), 22050)
+    assert y.dtype == np.float32 and np.abs(y - x).max() < 1e-4
+    wavfile.write(tmp_path / "b.wav", 44100, np.repeat((x * 32767).astype(np.int16), 2))
+    z = _load_audio(str(tmp_path / "b.wav"), 22050)
+    assert abs(len(z) - len(x)) <= 1
+    _write_audio(str(tmp_path / "o.npy"), x, 22050)
+    assert np.array_equal(np.load(tmp_path / "o.npy"), x)
+
+
+def test_lpt_shard_balances_and_covers():
+    from openvoice_b200.distributed import lpt_shard
+    costs = [10, 1, 7, 3, 3, 9, 2, 8]
+    for w in (1, 2, 3, 8, 11):
+        sh = lpt_shard(costs, w)
+        assert sorted(i for s in sh for i in s) == list(range(len(costs)))
+        loads = [sum(costs[i] for i in s) for s in sh]
+        assert max(loads) - min(l for l in loads if l or w <= len(costs)) <= max(costs)
+    assert lpt_shard(costs, 2) == lpt_shard(costs, 2)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from openvoice_b200.distributed import broadcast_state_dict, convert_sharded, lpt_shard
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sd = {"a.weight": torch.arange(12.).reshape(3, 4), "b.bias": torch.tensor([1.5, -2.0]), "c": torch.ones(2, 1, 3)} if rank == 0 else None
+got = broadcast_state_dict(sd)
+assert set(got) == {"a.weight", "b.bias", "c"} and got["a.weight"].shape == (3, 4) and float(got["a.weight"][2, 3]) == 11.0
+assert torch.equal(got["b.bias"], torch.tensor([1.5, -2.0]))
+rng = np.random.default_rng(0)
+audios = [rng.standard_normal(n).astype(np.float32) for n in (700, 50, 300, 1200, 256, 999, 10)]
+calls = []
+def fake_convert(batch, src, tgt, tau=0.3):
+    calls.append(len(batch))
+    return [(-a[: 256 * (len(a) // 256)] * tau).astype(np.float32) for a in batch]
+out = convert_sharded(fake_convert, audios, None, None, tau=0.5)
+mine = lpt_shard([len(a) for a in audios], world)[rank]
+assert calls == ([len(mine)] if mine else [])
+if rank == 0:
+    assert len(out) == len(audios)
+    for a, o in zip(audios, out):
+        assert np.array_equal(o, (-a[: 256 * (len(a) // 256)] * 0.5).astype(np.float32))
+else:
+    assert out is None
+dist.barrier()
+dist.destroy_process_group()
+print("worker", rank, "ok")
+"""
+
+
+def test_multi_gpu_driver_under_gloo_world2(tmp_path):
+    """The N>1 path (checkpoint broadcast, LPT sharding, waveform gather) with 2 CPU processes."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "worker 0 ok" in r.stdout and "worker 1 ok" in r.stdout
