@@ -10,7 +10,7 @@ GPU, every rank converts its own `batch` clips (weak scaling, no data-path colle
 broadcasts the checkpoint and, in the end-to-end leg, gathers the output waveforms on rank 0).
 
 One JSON line on stdout (rank 0):
-  value      device-resident: waveforms already in HBM -> spectrogram -> voice_conversion, CUDA events
+  value      device-resident: waveforms already in HBM -> ovc_convert_waveform (STFT + voice_conversion), CUDA events
   e2e        through ToneColorConverter.convert_batch with HOST numpy waveforms: pinned H2D, STFT,
              voice_conversion, D2H of the samples, all inside the timed region
   roofline   generator ResBlock conv family (90 % of the FLOPs): algorithmic layer-granular bytes
@@ -185,7 +185,6 @@ def main():
     import torch.distributed as dist
     from oracle import vc_oracle as O          # synthetic checkpoint recipe + cpu_baseline only
     from openvoice_b200.api import ToneColorConverter
-    from openvoice_b200.mel_processing import spectrogram_torch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -226,12 +225,10 @@ def main():
     src = torch.cat([synth_se(rank * B + i, 2000) for i in range(B)]).to(dev)
     tgt = torch.cat([synth_se(rank * B + i, 3000) for i in range(B)]).to(dev)
     wav_dev = torch.from_numpy(np.stack(waves)).to(dev)
-    lengths = torch.full((B,), T, dtype=torch.int64, device=dev)
-    hp = conv.hps.data
+    wav_len = torch.full((B,), L, dtype=torch.int64, device=dev)
 
     def device_step(seed):
-        spec = spectrogram_torch(wav_dev, hp.filter_length, hp.sampling_rate, hp.hop_length, hp.win_length).contiguous()
-        o, _, _ = conv.model.voice_conversion(spec, lengths, src, tgt, tau=0.3, seed=seed, ragged=True, latents=False)
+        o, _ = conv.model.native.convert_waveform(wav_dev, wav_len, src, tgt, tau=0.3, seed=seed)
         return o
 
     def barrier():

@@ -113,7 +113,26 @@ OVC_API int ovc_voice_conversion(ovc_ctx* ctx, const float* spec, const int64_t*
                          uint64_t seed, float tau, int B, int Tmax, int ragged,
                          float* o_hat, float* z, float* z_p, float* z_hat, void* stream);
 
-/* Number of kernels the last ovc_voice_conversion call on this context launched. */
+/* Front end of convert (row a2): linear magnitude spectrogram, replaces spectrogram_torch
+ * (openvoice/mel_processing.py:40-75; call sites api.py:126-128,150-152) for n_fft = win = 1024,
+ * hop 256: reflect-pad 384 at both ends of each item's own length, periodic hann, centre=False,
+ * sqrt(re^2 + im^2 + 1e-6).
+ *   wav          [B, Lmax] fp32 (device), rows zero padded past wav_lengths[b]
+ *   wav_lengths  [B] int64 samples (device), each > 384 (reflect padding) and <= Lmax
+ *   spec         [B, spec_channels, Tmax] out; frames >= wav_lengths[b]/hop are written as zeros
+ *   frames       [B] int64 out (nullable): min(Tmax, wav_lengths[b] / hop)                          */
+OVC_API int ovc_spectrogram(ovc_ctx* ctx, const float* wav, const int64_t* wav_lengths, int B, int Lmax,
+                            int Tmax, float* spec, int64_t* frames, void* stream);
+
+/* ToneColorConverter.convert's device work in one call (openvoice/api.py:148-155, batch of B):
+ * spectrogram -> voice_conversion with per-item exact lengths (ragged).  Tmax = Lmax / hop.
+ *   o_hat   [B, hop*Tmax] out; item b holds hop*frames[b] samples, zeros after
+ *   frames  [B] int64 out (nullable)                                                               */
+OVC_API int ovc_convert_waveform(ovc_ctx* ctx, const float* wav, const int64_t* wav_lengths, int B, int Lmax,
+                                 const float* g_src, const float* g_tgt, const float* noise, uint64_t seed,
+                                 float tau, float* o_hat, int64_t* frames, void* stream);
+
+/* Number of kernels the last ovc_voice_conversion / ovc_convert_waveform call launched. */
 OVC_API int ovc_last_launch_count(const ovc_ctx* ctx);
 
 /* Per-call timing hook for bench.py's roofline: when enabled, the dominant kernel family

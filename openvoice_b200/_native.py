@@ -18,6 +18,7 @@ EXPORTS = (
     "ovc_abi_version", "ovc_last_error", "ovc_create", "ovc_destroy", "ovc_load_tensor",
     "ovc_finalize_weights", "ovc_workspace_floats", "ovc_voice_conversion", "ovc_last_launch_count",
     "ovc_profile_enable", "ovc_profile_read", "ovc_debug_enable", "ovc_debug_fetch",
+    "ovc_spectrogram", "ovc_convert_waveform",
 )
 
 
@@ -70,6 +71,10 @@ def load_library(path: Optional[str] = None):
                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.ovc_debug_enable.argtypes = [C.c_void_p, C.c_int]
     lib.ovc_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
+    lib.ovc_spectrogram.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    lib.ovc_convert_waveform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.ovc_abi_version() != ABI_VERSION:
         raise OvcError(f"ABI mismatch: library {lib.ovc_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
@@ -194,6 +199,46 @@ class NativeConverter:
             C.c_void_p(st.cuda_stream))
         _check(self.lib, rc, "ovc_voice_conversion")
         return o, lat
+
+    def spectrogram(self, wav, wav_lengths, stream=None):
+        """wav [B, Lmax] f32 cuda (zero padded), wav_lengths [B] i64 cuda (samples) ->
+        (spec [B, S, Lmax // hop], frames [B] i64): spectrogram_torch on device, per-item reflect padding."""
+        import torch
+        assert wav.is_cuda and wav.dtype == torch.float32 and wav.is_contiguous() and wav.dim() == 2
+        assert wav_lengths.is_cuda and wav_lengths.dtype == torch.int64
+        B, L = wav.shape
+        T = L // self.hp.hop_length
+        spec = torch.empty(B, self.hp.spec_channels, T, device=wav.device, dtype=torch.float32)
+        frames = torch.empty(B, device=wav.device, dtype=torch.int64)
+        st = stream if stream is not None else torch.cuda.current_stream(wav.device)
+        rc = self.lib.ovc_spectrogram(self.handle, C.c_void_p(wav.data_ptr()), C.c_void_p(wav_lengths.data_ptr()), B, L, T,
+                                      C.c_void_p(spec.data_ptr()), C.c_void_p(frames.data_ptr()), C.c_void_p(st.cuda_stream))
+        _check(self.lib, rc, "ovc_spectrogram")
+        return spec, frames
+
+    def convert_waveform(self, wav, wav_lengths, g_src, g_tgt, noise=None, tau: float = 0.3, seed: int = 0, stream=None):
+        """The device work of ToneColorConverter.convert for a batch: wav [B, Lmax] f32 cuda ->
+        (o_hat [B, hop * (Lmax // hop)], frames [B]).  Asynchronous on `stream`."""
+        import torch
+        assert wav.is_cuda and wav.dtype == torch.float32 and wav.is_contiguous() and wav.dim() == 2
+        assert wav_lengths.is_cuda and wav_lengths.dtype == torch.int64
+        B, L = wav.shape
+        T = L // self.hp.hop_length
+        gs = g_src.reshape(B, -1).contiguous().float()
+        gt = g_tgt.reshape(B, -1).contiguous().float()
+        if noise is not None:
+            noise = noise.contiguous().float()
+            assert tuple(noise.shape) == (B, self.hp.inter_channels, T)
+        o = torch.empty(B, self.hp.hop_length * T, device=wav.device, dtype=torch.float32)
+        frames = torch.empty(B, device=wav.device, dtype=torch.int64)
+        st = stream if stream is not None else torch.cuda.current_stream(wav.device)
+        rc = self.lib.ovc_convert_waveform(
+            self.handle, C.c_void_p(wav.data_ptr()), C.c_void_p(wav_lengths.data_ptr()), B, L, C.c_void_p(gs.data_ptr()),
+            C.c_void_p(gt.data_ptr()), C.c_void_p(noise.data_ptr()) if noise is not None else None,
+            C.c_uint64(seed & (2 ** 64 - 1)), C.c_float(tau), C.c_void_p(o.data_ptr()), C.c_void_p(frames.data_ptr()),
+            C.c_void_p(st.cuda_stream))
+        _check(self.lib, rc, "ovc_convert_waveform")
+        return o, frames
 
     @property
     def last_launch_count(self) -> int:

@@ -189,9 +189,9 @@ class ToneColorConverter(OpenVoiceBaseClass):
         gs = []
         for fname in ref_wav_list:
             audio_ref = _load_audio(fname, hps.data.sampling_rate)
-            y = torch.from_numpy(audio_ref).to(self.device).unsqueeze(0)
-            y = spectrogram_torch(y, hps.data.filter_length, hps.data.sampling_rate, hps.data.hop_length,
-                                  hps.data.win_length, center=False)
+            y = torch.from_numpy(audio_ref).to(self.device).unsqueeze(0).contiguous()
+            n = torch.tensor([y.shape[1]], dtype=torch.int64, device=self.device)
+            y, _ = self.model.native.spectrogram(y, n)          # = spectrogram_torch (api.py:126-128)
             g = self.model.ref_enc(y.transpose(1, 2)).unsqueeze(-1)
             gs.append(g.detach())
         gs = torch.stack(gs).mean(0)
@@ -253,34 +253,28 @@ class ToneColorConverter(OpenVoiceBaseClass):
             raise ValueError("audio shorter than one hop")
         Tmax = max(frames)
         dev = self.device
+        if min(len(w) for w in waves) <= (hps.data.filter_length - hop) // 2:
+            raise ValueError("audio shorter than the STFT reflect padding")   # torch raises here too
         # host -> device: one pinned staging buffer, one copy
         Lmax = max(len(w) for w in waves)
         stage = torch.zeros(B, Lmax, dtype=torch.float32).pin_memory()
         for b, w in enumerate(waves):
             stage[b, : len(w)] = torch.from_numpy(w)
         wav = stage.to(dev, non_blocking=True)
-        spec = torch.zeros(B, hps.data.filter_length // 2 + 1, Tmax, device=dev, dtype=torch.float32)
-        if len(set(len(w) for w in waves)) == 1:
-            spec = spectrogram_torch(wav, hps.data.filter_length, hps.data.sampling_rate, hop,
-                                     hps.data.win_length, center=False).contiguous()
-        else:   # reflect padding happens at each utterance's own end
-            for b, w in enumerate(waves):
-                s = spectrogram_torch(wav[b: b + 1, : len(w)], hps.data.filter_length, hps.data.sampling_rate,
-                                      hop, hps.data.win_length, center=False)
-                spec[b, :, : s.shape[2]] = s[0]
-        lengths = torch.tensor(frames, dtype=torch.int64).to(dev, non_blocking=True)
+        wlen = torch.tensor([len(w) for w in waves], dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
         nz = None
         if noise is not None:
             nz = torch.zeros(B, hps.model.inter_channels, Tmax, device=dev, dtype=torch.float32)
             for b, q in enumerate(noise):
                 q = q.reshape(hps.model.inter_channels, -1)
                 nz[b, :, : q.shape[1]] = q.to(dev)
-        o, _, _ = self.model.voice_conversion(spec, lengths, src, tgt, tau=tau, noise=nz, ragged=True,
-                                              latents=False)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        # spectrogram + voice_conversion, every item at its own exact length (api.py:148-154)
+        o, _ = self.model.native.convert_waveform(wav, wlen, src, tgt, noise=nz, tau=float(tau), seed=seed)
         host = torch.empty(o.shape, dtype=torch.float32).pin_memory()
         host.copy_(o, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        audio = host[:, 0].numpy()
+        audio = host.numpy()
         return [audio[b, : frames[b] * hop].copy() for b in range(B)]
 
     # ------------------------------------------------------------------ watermark (third-party model)

@@ -25,10 +25,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef OVC_FFMA2
+#define OVC_FFMA2 1   // 1: packed fma.rn.f32x2 inner loop (Blackwell FFMA2); 0: scalar FFMA
+#endif
+
 namespace ovc {
 
 enum EpiKind : int {
-  EPI_LINEAR = 0,   // y = (conv + bias [+ res] [+ y_old]) / div          (pre, conv_pre, ResBlock1 convs)
+  EPI_LINEAR = 0,   // y = (conv + bias [+ res] [+ y_old]) * scale         (pre, conv_pre, ResBlock1 convs)
   EPI_GATE = 1,     // y = tanh(a + g_a) * sigmoid(b + g_b)               (WN in_layer; commons.py:100-107)
   EPI_RESSKIP = 2,  // x += rs[:H] ; skip (+)= rs[H:]                     (WN res_skip; modules.py:203-209)
   EPI_PROJ = 3,     // z = m + noise * tau * exp(logs)                    (enc_q.proj; models.py:218-220)
@@ -53,7 +57,7 @@ struct ConvArgs {
   // per-utterance valid lengths (frames); NULL -> tmax.  limits = base * mul
   const long long* lens_in; const long long* lens_out; int tmax; int mul_in; int mul_out;
   float slope;      // leaky_relu slope applied to X while staging (1 = identity)
-  float div;        // LINEAR: divide result (3 for the last MRF accumulation, else 1)
+  float scale;      // LINEAR: multiply the result (1/3 for the last MRF accumulation, else 1)
   float tau;        // PROJ
   float sign;       // COUPLE: +1 forward, -1 reverse
   int flags;        // F_ACCUM, F_FIRST
@@ -161,7 +165,7 @@ struct ConvCfg {
   static constexpr int HL = G::HL, HR = G::HR;
   static constexpr int XW = HL + T_T + HR;               // smem row width in floats (multiple of 4)
   static constexpr int W_STAGE = CI_CH * K * CO_T;       // floats
-  static constexpr int X_STAGE = CI_CH * XW;             // floats
+  static constexpr int X_STAGE = CI_CH * XW;             // floats (compact)
   static constexpr size_t SMEM_BYTES = 16 + sizeof(float) * 2 * (W_STAGE + X_STAGE);
   static constexpr int MIN_BLOCKS = (THREADS >= 256) ? 2 : (THREADS >= 128 ? 3 : 4);
 };
@@ -176,6 +180,66 @@ __host__ __device__ constexpr bool tap_is_zero(int k, int r) {
   return false;
 }
 
+#if OVC_FFMA2
+typedef unsigned long long u64;
+// d.lo += a.lo * x ; d.hi += a.hi * x  -- ptxas folds the {x, x} pack into the FFMA2 scalar-broadcast
+// operand form (SASS: FFMA2 Rd, Ra.F32x2.HI_LO, Rx.F32, Rd.F32x2.HI_LO), so it costs no instruction.
+__device__ __forceinline__ void fma2_bcast(u64& d, const u64 a, const float x) {
+  u64 xx;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(xx));
+}
+template <int EPI>
+__host__ __device__ constexpr bool pair_is_zero(int k, int rp) {
+  if (EPI == EPI_UPS8) return (k == 0 && rp >= 2) || (k == 2 && rp < 2);
+  return false;   // stride-2 polyphase rows alternate inside a pair: the packed zeros are multiplied
+}
+
+// one tap group of one 4-wide time chunk, packed: acc[rp][j] holds rows (2rp, 2rp+1) at time j
+template <class C, int G>
+__device__ __forceinline__ void tap_group(u64 (&acc)[4][4], const float* __restrict__ xrow,
+                                          const float* __restrict__ wrow) {
+  using TG = typename C::G;
+  constexpr int NV = TG::nvec(G);
+  constexpr int LO = TG::lo(G);
+  float win[4 * NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(xrow + LO + 4 * i);
+    win[4 * i + 0] = v.x; win[4 * i + 1] = v.y; win[4 * i + 2] = v.z; win[4 * i + 3] = v.w;
+  }
+#pragma unroll
+  for (int k = TG::k_lo(G); k < TG::k_hi(G); ++k) {
+    const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(wrow + k * C::CO_T);
+    const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(wrow + k * C::CO_T + 4);
+    const u64 w2[4] = {wa.x, wa.y, wb.x, wb.y};   // rows (0,1) (2,3) (4,5) (6,7)
+    const int base = TG::off(k) - LO;
+#pragma unroll
+    for (int rp = 0; rp < 4; ++rp) {
+      if (pair_is_zero<C::EPI>(k, rp)) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fma2_bcast(acc[rp][j], w2[rp], win[base + j]);
+    }
+  }
+}
+
+template <class C>
+__device__ __forceinline__ void compute_chunk(u64 (&acc)[2][4][4], const float* __restrict__ xs,
+                                              const float* __restrict__ ws, int tb, int cb) {
+#pragma unroll 1
+  for (int ci = 0; ci < C::CI_CH; ++ci) {
+    const float* wrow = ws + ci * (C::K * C::CO_T) + cb;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float* xrow = xs + ci * C::XW + C::HL + tb + 32 * c;
+      tap_group<C, 0>(acc[c], xrow, wrow);
+      if constexpr (C::NG >= 2) tap_group<C, 1>(acc[c], xrow, wrow);
+      if constexpr (C::NG >= 3) tap_group<C, 2>(acc[c], xrow, wrow);
+      if constexpr (C::NG >= 4) tap_group<C, 3>(acc[c], xrow, wrow);
+    }
+  }
+}
+#else
 // one tap group of one 4-wide time chunk: load the X window, run the taps
 template <class C, int G>
 __device__ __forceinline__ void tap_group(float (&acc)[8][4], const float* __restrict__ xrow,
@@ -216,9 +280,11 @@ __device__ __forceinline__ void compute_chunk(float (&acc)[2][8][4], const float
       tap_group<C, 0>(acc[c], xrow, wrow);
       if constexpr (C::NG >= 2) tap_group<C, 1>(acc[c], xrow, wrow);
       if constexpr (C::NG >= 3) tap_group<C, 2>(acc[c], xrow, wrow);
+      if constexpr (C::NG >= 4) tap_group<C, 3>(acc[c], xrow, wrow);
     }
   }
 }
+#endif
 
 // stage one ci-chunk of X: rows [ci0, ci0+CI_CH), time [t0-HL, t0+T_T+HR)
 template <class C>
@@ -312,13 +378,23 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) conv1d_f32(const Co
   stage_x_activate<C>(xsm, a.slope);
   __syncthreads();
 
-  float acc[2][8][4];
+#if OVC_FFMA2
+  u64 accw[2][4][4];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) accw[c][r][j] = 0ull;
+#else
+  float accw[2][8][4];
 #pragma unroll
   for (int c = 0; c < 2; ++c)
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[c][r][j] = 0.f;
+      for (int j = 0; j < 4; ++j) accw[c][r][j] = 0.f;
+#endif
 
   const int n_chunks = a.n_chunks;
   for (int ch = 0; ch < n_chunks; ++ch) {
@@ -331,13 +407,28 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) conv1d_f32(const Co
       stage_x_async<C>(xsm + (s ^ 1) * C::X_STAGE, xb, a.x_pitch, a.cin, (ch + 1) * C::CI_CH, t0, in_lim);
     }
     mbar_wait(&bars[s], (ch >> 1) & 1);
-    compute_chunk<C>(acc, xsm + s * C::X_STAGE, wsm + s * C::W_STAGE, tb, cb);
+    compute_chunk<C>(accw, xsm + s * C::X_STAGE, wsm + s * C::W_STAGE, tb, cb);
     if (ch + 1 < n_chunks) {
       cp_async_wait_all();
       stage_x_activate<C>(xsm + (s ^ 1) * C::X_STAGE, a.slope);
     }
     __syncthreads();
   }
+
+#if OVC_FFMA2
+  float acc[2][8][4];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int rp = 0; rp < 4; ++rp)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[c][2 * rp][j] = __uint_as_float((unsigned)(accw[c][rp][j] & 0xffffffffull));
+        acc[c][2 * rp + 1][j] = __uint_as_float((unsigned)(accw[c][rp][j] >> 32));
+      }
+#else
+  float (&acc)[2][8][4] = accw;
+#endif
 
   // ------------------------------------------------------------------ epilogue
   const int row0 = blockIdx.y * C::CO_T + cb;   // first packed row of this thread
@@ -366,9 +457,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) conv1d_f32(const Co
             const float4 q = *reinterpret_cast<const float4*>(yp);
             v[0] = q.x + v[0]; v[1] = q.y + v[1]; v[2] = q.z + v[2]; v[3] = q.w + v[3];
           }
-          if (a.div != 1.f) {
+          if (a.scale != 1.f) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = v[j] / a.div;
+            for (int j = 0; j < 4; ++j) v[j] = v[j] * a.scale;
           }
           *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
@@ -378,7 +469,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) conv1d_f32(const Co
               float u = v[j];
               if (rb) u += rb[(size_t)(row0 + r) * a.r_pitch + t + j];
               if (accum) u = yp[j] + u;
-              if (a.div != 1.f) u = u / a.div;
+              if (a.scale != 1.f) u = u * a.scale;
               yp[j] = u;
             }
           }

@@ -105,7 +105,7 @@ struct ovc_ctx {
   std::vector<float> h_w;   // staging while packing
 
   // layers
-  ConvLayer enc_pre, enc_proj;
+  ConvLayer enc_pre, enc_pre16, enc_proj;
   WNLayers enc_wn;
   ConvLayer flow_pre[4], flow_post[4];
   WNLayers flow_wn[4];
@@ -118,6 +118,10 @@ struct ovc_ctx {
   int* d_cond_sel = nullptr;
   int cond_rows_out = 0;
   int cond_off_enc = 0, cond_off_fsrc = 0, cond_off_ftgt = 0, cond_off_dec = 0;
+
+  // STFT tables (twiddles exp(-2 pi i m / 1024), periodic hann window)
+  float2* d_tw = nullptr;
+  float* d_win = nullptr;
 
   // workspace
   float* d_ws = nullptr;
@@ -290,6 +294,8 @@ static int finalize(ovc_ctx* c) {
     if (w->shape.size() != 3 || w->shape[0] != H || w->shape[1] != S) return fail(OVC_ERR_INVALID, "enc_q.pre.weight has the wrong shape");
     c->enc_pre = pack_conv(c, V_ENC_PRE, H, S, [&](int p, int ci, int) { return w->data[(size_t)p * S + ci]; },
                            [&](int p) { return b->data[p]; }, H, 1, H);
+    c->enc_pre16 = c->enc_pre;            // same packing, 16-byte cp.async when the spectrogram pitch allows it
+    c->enc_pre16.variant = V_FLOW_PRE;
     if (pack_wn(c, "enc_q.enc", 16, &c->enc_wn, &miss)) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
     NEED(pw, "enc_q.proj.weight");
     NEED(pb, "enc_q.proj.bias");
@@ -441,6 +447,19 @@ static int finalize(ovc_ctx* c) {
   CK(cudaMalloc(&c->d_cond_sel, sel.size() * sizeof(int)));
   CK(cudaMemcpy(c->d_cond_wrow, wrow.data(), wrow.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_cond_sel, sel.data(), sel.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (!c->d_tw) {
+    std::vector<float2> tw(STFT_N);
+    std::vector<float> win(STFT_N);
+    const double PI = 3.14159265358979323846;
+    for (int m = 0; m < STFT_N; ++m) {
+      tw[m] = make_float2((float)std::cos(2.0 * PI * m / STFT_N), (float)(-std::sin(2.0 * PI * m / STFT_N)));
+      win[m] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * m / STFT_N));   // torch.hann_window(periodic=True)
+    }
+    CK(cudaMalloc(&c->d_tw, STFT_N * sizeof(float2)));
+    CK(cudaMalloc(&c->d_win, STFT_N * sizeof(float)));
+    CK(cudaMemcpy(c->d_tw, tw.data(), STFT_N * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_win, win.data(), STFT_N * sizeof(float), cudaMemcpyHostToDevice));
+  }
   c->h_w.clear();
   c->h_w.shrink_to_fit();
   c->sd.clear();
@@ -454,7 +473,7 @@ static int finalize(ovc_ctx* c) {
 // ---------------------------------------------------------------------------------------------
 struct WsLayout {
   int P;   // frame pitch (multiple of 4)
-  size_t cond, x, skip, acts, z, dpre, bufA, bufB, bufC, bufD, total;
+  size_t cond, x, skip, acts, z, dpre, bufA, bufB, bufC, bufD, spec, frames, total;
 };
 static WsLayout ws_layout(const ovc_ctx* c, int B, int Tmax) {
   WsLayout L;
@@ -472,9 +491,17 @@ static WsLayout ws_layout(const ovc_ctx* c, int B, int Tmax) {
   L.bufB = take(big);
   L.bufC = take(big);
   L.bufD = take(big);
+  L.spec = take((size_t)B * c->hp.spec_channels * L.P);
+  L.frames = take((size_t)2 * B + 4);   // B int64
   L.total = o;
   return L;
 }
+
+#define TRY(expr)                   \
+  do {                              \
+    int rc_ = (expr);               \
+    if (rc_ != OVC_OK) return rc_;  \
+  } while (0)
 
 struct Run {
   ovc_ctx* c;
@@ -491,7 +518,7 @@ static int launch(Run& r, const ConvLayer& L, ConvArgs a, int t_len, bool profil
   a.n_chunks = L.n_chunks;
   a.cin = L.cin;
   a.tmax = r.Tmax;
-  if (a.div == 0.f) a.div = 1.f;
+  if (a.scale == 0.f) a.scale = 1.f;
   ovc_ctx* c = r.c;
   const bool prof = profiled && c->prof;
   if (prof) {
@@ -528,11 +555,6 @@ static int tap(Run& r, const char* name, const float* src, int C, int T, int pit
   return OVC_OK;
 }
 
-#define TRY(expr)                   \
-  do {                              \
-    int rc_ = (expr);               \
-    if (rc_ != OVC_OK) return rc_;  \
-  } while (0)
 
 // one WN stack (modules.py:185-210): x <- in place, skip <- output
 static int run_wn(Run& r, const WNLayers& wn, float* x, float* skip, float* acts, const float* cond, int cond_bs) {
@@ -579,7 +601,7 @@ static int run_flow(Run& r, const WsLayout& W, float* ws, bool reverse, const fl
     a.bias = c->d_w + c->flow_pre[f].b_off; a.bias_bs = 0;
     a.y = x; a.y_bs = bs; a.y_pitch = P;
     a.lens_in = r.lens; a.lens_out = r.lens; a.mul_in = 1; a.mul_out = 1;
-    a.slope = 1.f; a.div = 1.f;
+    a.slope = 1.f; a.scale = 1.f;
     TRY(launch(r, c->flow_pre[f], a, T));
     TRY(run_wn(r, c->flow_wn[f], x, skip, acts, cond_all + sect + f * 4 * 384, c->cond_rows_out));
     // post + coupling update of x1 in place                                (modules.py:441-454)
@@ -595,23 +617,27 @@ static int run_flow(Run& r, const WsLayout& W, float* ws, bool reverse, const fl
   return OVC_OK;
 }
 
-static int run_vc(ovc_ctx* c, const float* spec, const long long* lens, const float* g_src, const float* g_tgt,
+static int ensure_ws(ovc_ctx* c, const WsLayout& W, int B, int Tmax, cudaStream_t st) {
+  if (W.total <= c->ws_floats) return OVC_OK;
+  CK(cudaStreamSynchronize(st));
+  if (c->d_ws) CK(cudaFree(c->d_ws));
+  c->d_ws = nullptr;
+  c->ws_floats = 0;
+  cudaError_t e = cudaMalloc(&c->d_ws, W.total * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(OVC_ERR_NOMEM, "workspace of %.2f GB for B=%d Tmax=%d does not fit: %s", W.total * 4e-9, B, Tmax,
+                cudaGetErrorString(e));
+  }
+  c->ws_floats = W.total;
+  return OVC_OK;
+}
+
+static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long* lens, const float* g_src, const float* g_tgt,
                   const float* noise, uint64_t seed, float tau, int B, int Tmax, int ragged, float* o_hat,
                   float* z_out, float* zp_out, float* zh_out, cudaStream_t st) {
   const WsLayout W = ws_layout(c, B, Tmax);
-  if (W.total > c->ws_floats) {
-    CK(cudaStreamSynchronize(st));
-    if (c->d_ws) CK(cudaFree(c->d_ws));
-    c->d_ws = nullptr;
-    c->ws_floats = 0;
-    cudaError_t e = cudaMalloc(&c->d_ws, W.total * sizeof(float));
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return fail(OVC_ERR_NOMEM, "workspace of %.2f GB for B=%d Tmax=%d does not fit: %s", W.total * 4e-9, B, Tmax,
-                  cudaGetErrorString(e));
-    }
-    c->ws_floats = W.total;
-  }
+  TRY(ensure_ws(c, W, B, Tmax, st));
   float* ws = c->d_ws;
   Run r{c, st, B, Tmax, W.P, lens, ragged ? lens : nullptr, (double)B * Tmax};
   c->launches = 0;
@@ -636,12 +662,13 @@ static int run_vc(ovc_ctx* c, const float* spec, const long long* lens, const fl
   // ---- posterior encoder (models.py:212-221)
   {
     ConvArgs a{};
-    a.x = spec; a.x_bs = (long long)c->hp.spec_channels * Tmax; a.x_pitch = Tmax;
+    a.x = spec; a.x_bs = (long long)c->hp.spec_channels * spec_pitch; a.x_pitch = spec_pitch;
     a.bias = c->d_w + c->enc_pre.b_off; a.bias_bs = 0;
     a.y = ws + W.x; a.y_bs = bs192; a.y_pitch = P;
     a.lens_in = lens; a.lens_out = lens; a.mul_in = 1; a.mul_out = 1;
-    a.slope = 1.f; a.div = 1.f;
-    TRY(launch(r, c->enc_pre, a, Tmax));
+    a.slope = 1.f; a.scale = 1.f;
+    const bool aligned = (spec_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(spec) & 15) == 0);
+    TRY(launch(r, aligned ? c->enc_pre16 : c->enc_pre, a, Tmax));
     TRY(tap(r, "enc.pre", ws + W.x, 192, Tmax, P));
     TRY(run_wn(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, cond + c->cond_off_enc, c->cond_rows_out));
     TRY(tap(r, "enc.wn", ws + W.skip, 192, Tmax, P));
@@ -677,7 +704,7 @@ static int run_vc(ovc_ctx* c, const float* spec, const long long* lens, const fl
     a.y = ws + W.dpre; a.y_bs = 512LL * P; a.y_pitch = P;
     a.lens_in = lens;          // z_hat * y_mask
     a.lens_out = r.glens; a.mul_in = 1; a.mul_out = 1;
-    a.slope = 1.f; a.div = 1.f;
+    a.slope = 1.f; a.scale = 1.f;
     TRY(launch(r, c->dec_pre, a, Tmax));
     TRY(tap(r, "dec.pre", ws + W.dpre, 512, Tmax, P));
   }
@@ -715,20 +742,20 @@ static int run_vc(ovc_ctx* c, const float* spec, const long long* lens, const fl
         a.bias = c->d_w + c->rb_c1[i * 3 + j][d].b_off; a.bias_bs = 0;
         a.y = bufC; a.y_bs = bsC; a.y_pitch = pitch_out;
         a.lens_in = r.glens; a.lens_out = r.glens; a.mul_in = up_out; a.mul_out = up_out;
-        a.slope = 0.1f; a.div = 1.f;
+        a.slope = 0.1f; a.scale = 1.f;
         TRY(launch(r, c->rb_c1[i * 3 + j][d], a, Tlen, true, fl, by));
         ConvArgs b{};
         b.x = bufC; b.x_bs = bsC; b.x_pitch = pitch_out;
         b.bias = c->d_w + c->rb_c2[i * 3 + j][d].b_off; b.bias_bs = 0;
         b.r = xin; b.r_bs = bsC; b.r_pitch = pitch_out;
         b.lens_in = r.glens; b.lens_out = r.glens; b.mul_in = up_out; b.mul_out = up_out;
-        b.slope = 0.1f; b.div = 1.f;
+        b.slope = 0.1f; b.scale = 1.f;
         if (d < 2) {
           b.y = bufB; b.y_bs = bsC; b.y_pitch = pitch_out;
         } else {
           b.y = bufD; b.y_bs = bsC; b.y_pitch = pitch_out;
           if (j > 0) b.flags = F_ACCUM;
-          if (j == 2) b.div = 3.f;
+          if (j == 2) b.scale = 1.0f / 3.0f;   // xs / num_kernels (models.py:286), as a multiply
         }
         TRY(launch(r, c->rb_c2[i * 3 + j][d], b, Tlen, true, fl, by));
       }
@@ -793,6 +820,8 @@ void ovc_destroy(ovc_ctx* c) {
   if (c->d_ws) cudaFree(c->d_ws);
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
+  if (c->d_tw) cudaFree(c->d_tw);
+  if (c->d_win) cudaFree(c->d_win);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& kv : c->taps)
     if (kv.second.d) cudaFree(kv.second.d);
@@ -834,8 +863,52 @@ int ovc_voice_conversion(ovc_ctx* c, const float* spec, const int64_t* lengths, 
   if (B > 65535) return fail(OVC_ERR_INVALID, "B %d exceeds the grid limit", B);
   CK(cudaSetDevice(c->device));
   c->ev_used = c->prof ? c->ev_used : 0;
-  return run_vc(c, spec, (const long long*)lengths, g_src, g_tgt, noise, seed, tau, B, Tmax, ragged, o_hat, z, z_p, z_hat,
+  return run_vc(c, spec, Tmax, (const long long*)lengths, g_src, g_tgt, noise, seed, tau, B, Tmax, ragged, o_hat, z, z_p, z_hat,
                 (cudaStream_t)stream);
+}
+
+static int launch_stft(ovc_ctx* c, const float* wav, const int64_t* wav_lengths, int B, int Lmax, int Tmax, float* spec,
+                       int spec_pitch, long long* frames, cudaStream_t st) {
+  if (c->hp.spec_channels != STFT_N / 2 + 1 || c->hp.hop_length != 256)
+    return fail(OVC_ERR_INVALID, "the STFT kernel is specialised for n_fft = win_length = 1024, hop 256");
+  dim3 grid((Tmax + STFT_FR - 1) / STFT_FR, B);
+  stft_mag_kernel<<<grid, 256, 0, st>>>(wav, (long long)Lmax, (const long long*)wav_lengths, c->hp.hop_length, spec,
+                                        (long long)c->hp.spec_channels * spec_pitch, spec_pitch, Tmax, c->d_tw, c->d_win,
+                                        frames);
+  CK(cudaGetLastError());
+  return OVC_OK;
+}
+
+int ovc_spectrogram(ovc_ctx* c, const float* wav, const int64_t* wav_lengths, int B, int Lmax, int Tmax, float* spec,
+                    int64_t* frames, void* stream) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  if (!c->finalized) return fail(OVC_ERR_STATE, "ovc_finalize_weights has not been called");
+  if (!wav || !wav_lengths || !spec) return fail(OVC_ERR_INVALID, "null tensor argument");
+  if (B < 1 || Lmax < 1 || Tmax < 1 || B > 65535) return fail(OVC_ERR_INVALID, "bad sizes B=%d Lmax=%d Tmax=%d", B, Lmax, Tmax);
+  CK(cudaSetDevice(c->device));
+  return launch_stft(c, wav, wav_lengths, B, Lmax, Tmax, spec, Tmax, (long long*)frames, (cudaStream_t)stream);
+}
+
+int ovc_convert_waveform(ovc_ctx* c, const float* wav, const int64_t* wav_lengths, int B, int Lmax, const float* g_src,
+                         const float* g_tgt, const float* noise, uint64_t seed, float tau, float* o_hat, int64_t* frames,
+                         void* stream) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  if (!c->finalized) return fail(OVC_ERR_STATE, "ovc_finalize_weights has not been called");
+  if (!wav || !wav_lengths || !g_src || !g_tgt || !o_hat) return fail(OVC_ERR_INVALID, "null tensor argument");
+  const int Tmax = Lmax / c->hp.hop_length;
+  if (B < 1 || Tmax < 1 || B > 65535) return fail(OVC_ERR_INVALID, "bad sizes B=%d Lmax=%d", B, Lmax);
+  if ((long long)Tmax * 256 * 64 > 2000000000LL) return fail(OVC_ERR_INVALID, "Lmax %d too large for 32-bit indexing", Lmax);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const WsLayout W = ws_layout(c, B, Tmax);
+  TRY(ensure_ws(c, W, B, Tmax, st));
+  float* spec = c->d_ws + W.spec;
+  long long* fr = reinterpret_cast<long long*>(c->d_ws + W.frames);
+  TRY(launch_stft(c, wav, wav_lengths, B, Lmax, Tmax, spec, W.P, fr, st));
+  if (frames) CK(cudaMemcpyAsync(frames, fr, (size_t)B * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+  const int rc = run_vc(c, spec, W.P, fr, g_src, g_tgt, noise, seed, tau, B, Tmax, 1, o_hat, nullptr, nullptr, nullptr, st);
+  c->launches += 1;
+  return rc;
 }
 
 int ovc_last_launch_count(const ovc_ctx* c) { return c ? c->launches : 0; }

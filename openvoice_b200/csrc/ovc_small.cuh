@@ -107,4 +107,80 @@ __global__ void __launch_bounds__(256) copy_latent_kernel(const float* __restric
   dst[((size_t)b * C + c) * tmax + t] = v;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// stft_mag_kernel: the linear-spectrogram front end of convert (mel_processing.py:40-75):
+// reflect-pad (n_fft-hop)/2 = 384 at BOTH ends of each utterance's own length, periodic hann,
+// 1024-point DFT, centre=False, sqrt(re^2 + im^2 + 1e-6).  One CTA transforms 8 consecutive
+// frames (radix-4 Stockham FFT in shared memory, twiddles and window from host-computed
+// double-precision tables) and writes a [513][8] block so rows are stored 32 B at a time.
+// Frames past an utterance's T = L / hop are written as zeros.
+// ---------------------------------------------------------------------------------------------
+constexpr int STFT_N = 1024, STFT_FR = 8;
+
+__global__ void __launch_bounds__(256) stft_mag_kernel(const float* __restrict__ wav, long long wav_bs,
+                                                       const long long* __restrict__ wav_len, int hop,
+                                                       float* __restrict__ spec, long long spec_bs, int spec_pitch,
+                                                       int Tmax, const float2* __restrict__ tw,
+                                                       const float* __restrict__ win, long long* __restrict__ frames_out) {
+  __shared__ float2 buf[2][STFT_N];
+  __shared__ float mag[STFT_N / 2 + 1][STFT_FR + 1];
+  __shared__ float2 tws[STFT_N];
+  const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * STFT_FR;
+  const int L = (int)wav_len[b];
+  const int T = min(Tmax, L / hop);
+  if (blockIdx.x == 0 && tid == 0 && frames_out) frames_out[b] = T;
+  for (int i = tid; i < STFT_N; i += 256) tws[i] = tw[i];
+  const float* w = wav + (size_t)b * wav_bs;
+  const int pad = (STFT_N - hop) / 2;
+  for (int fr = 0; fr < STFT_FR; ++fr) {
+    const int t = t0 + fr;
+    if (t < T) {   // block-uniform
+      for (int n = tid; n < STFT_N; n += 256) {
+        int idx = t * hop + n - pad;
+        if (idx < 0) idx = -idx;
+        if (idx >= L) idx = 2 * (L - 1) - idx;
+        buf[0][n] = make_float2(w[idx] * win[n], 0.f);
+      }
+      __syncthreads();
+      int src = 0;
+#pragma unroll
+      for (int Ns = 1; Ns < STFT_N; Ns *= 4) {
+        const float2* in = buf[src];
+        float2* out = buf[src ^ 1];
+        const int k = tid & (Ns - 1);
+        const int j0 = ((tid - k) << 2) + k;
+        const int tstep = k * (256 / Ns);
+        float2 u0 = in[tid], u1 = in[tid + 256], u2 = in[tid + 512], u3 = in[tid + 768];
+        const float2 w1 = tws[tstep], w2 = tws[2 * tstep], w3 = tws[3 * tstep];
+        u1 = make_float2(u1.x * w1.x - u1.y * w1.y, u1.x * w1.y + u1.y * w1.x);
+        u2 = make_float2(u2.x * w2.x - u2.y * w2.y, u2.x * w2.y + u2.y * w2.x);
+        u3 = make_float2(u3.x * w3.x - u3.y * w3.y, u3.x * w3.y + u3.y * w3.x);
+        const float2 v0 = make_float2(u0.x + u2.x, u0.y + u2.y), v1 = make_float2(u0.x - u2.x, u0.y - u2.y);
+        const float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
+        const float2 d = make_float2(u1.x - u3.x, u1.y - u3.y);
+        const float2 v3 = make_float2(d.y, -d.x);   // (u1 - u3) * (-i)
+        out[j0] = make_float2(v0.x + v2.x, v0.y + v2.y);
+        out[j0 + Ns] = make_float2(v1.x + v3.x, v1.y + v3.y);
+        out[j0 + 2 * Ns] = make_float2(v0.x - v2.x, v0.y - v2.y);
+        out[j0 + 3 * Ns] = make_float2(v1.x - v3.x, v1.y - v3.y);
+        src ^= 1;
+        __syncthreads();
+      }
+      for (int f = tid; f <= STFT_N / 2; f += 256) {
+        const float2 c = buf[src][f];
+        mag[f][fr] = sqrtf(c.x * c.x + c.y * c.y + 1e-6f);
+      }
+    } else {
+      for (int f = tid; f <= STFT_N / 2; f += 256) mag[f][fr] = 0.f;
+    }
+    __syncthreads();
+  }
+  float* sp = spec + (size_t)b * spec_bs;
+  for (int e = tid; e < (STFT_N / 2 + 1) * STFT_FR; e += 256) {
+    const int f = e / STFT_FR, fr = e % STFT_FR;
+    if (t0 + fr < Tmax) sp[(size_t)f * spec_pitch + t0 + fr] = mag[f][fr];
+  }
+}
+
 }  // namespace ovc

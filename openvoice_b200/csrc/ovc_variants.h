@@ -25,8 +25,8 @@
   X(A_K7D5, 7, 5, 4, 2, 4, EPI_LINEAR, 2, 16)
 #define OVC_VARIANTS_G2(X)                                  \
   X(A_K11D1, 11, 1, 4, 2, 4, EPI_LINEAR, 1, 16)             \
-  X(A_K11D3, 11, 3, 4, 2, 4, EPI_LINEAR, 2, 16)             \
-  X(A_K11D5, 11, 5, 4, 2, 4, EPI_LINEAR, 3, 16)
+  X(A_K11D3, 11, 3, 4, 2, 4, EPI_LINEAR, 3, 16)             \
+  X(A_K11D5, 11, 5, 4, 2, 4, EPI_LINEAR, 4, 16)
 
 // generator, class B: 64 rows x 256 samples (C = 64)
 #define OVC_VARIANTS_G3(X)                                  \
@@ -38,8 +38,8 @@
   X(B_K7D5, 7, 5, 2, 4, 8, EPI_LINEAR, 2, 16)
 #define OVC_VARIANTS_G4(X)                                  \
   X(B_K11D1, 11, 1, 2, 4, 8, EPI_LINEAR, 1, 16)             \
-  X(B_K11D3, 11, 3, 2, 4, 8, EPI_LINEAR, 2, 16)             \
-  X(B_K11D5, 11, 5, 2, 4, 8, EPI_LINEAR, 3, 16)
+  X(B_K11D3, 11, 3, 2, 4, 8, EPI_LINEAR, 3, 16)             \
+  X(B_K11D5, 11, 5, 2, 4, 8, EPI_LINEAR, 4, 16)
 
 // generator, class C: 32 rows x 512 samples (C = 32)
 #define OVC_VARIANTS_G5(X)                                  \
@@ -51,8 +51,8 @@
   X(C_K7D5, 7, 5, 1, 8, 8, EPI_LINEAR, 2, 16)
 #define OVC_VARIANTS_G6(X)                                  \
   X(C_K11D1, 11, 1, 1, 8, 8, EPI_LINEAR, 1, 16)             \
-  X(C_K11D3, 11, 3, 1, 8, 8, EPI_LINEAR, 2, 16)             \
-  X(C_K11D5, 11, 5, 1, 8, 8, EPI_LINEAR, 3, 16)
+  X(C_K11D3, 11, 3, 1, 8, 8, EPI_LINEAR, 3, 16)             \
+  X(C_K11D5, 11, 5, 1, 8, 8, EPI_LINEAR, 4, 16)
 
 #define OVC_VARIANTS_ALL(X) \
   OVC_VARIANTS_G0(X) OVC_VARIANTS_G1(X) OVC_VARIANTS_G2(X) OVC_VARIANTS_G3(X) OVC_VARIANTS_G4(X) \

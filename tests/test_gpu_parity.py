@@ -138,6 +138,29 @@ def test_in_kernel_noise_statistics(native):
     assert abs(float((eps ** 3).mean())) < 0.05 and abs(float((eps ** 4).mean()) - 3.0) < 0.15
 
 
+def test_spectrogram_kernel(native):
+    """ovc_spectrogram vs the reference's spectrogram_torch output (golden) and vs the oracle on a
+    ragged batch (reflect padding at each item's own end)."""
+    d = np.load(os.path.join(GOLD, "convert_wave.npz"))
+    L = int(d["L"])
+    rng = np.random.default_rng(1000)
+    wav = (0.5 * (2 * rng.random(L, dtype=np.float32) - 1)).astype(np.float32)
+    spec, frames = native.native.spectrogram(torch.from_numpy(wav)[None].cuda(), torch.tensor([L]).cuda())
+    assert int(frames[0]) == L // 256 and spec.shape == (1, 513, L // 256)
+    assert rel_err(spec.cpu().numpy(), d["spec"]) < 2e-5
+    lens = [L, 385, 256 * 9 + 255, 256 * 17]
+    batch = torch.zeros(len(lens), L)
+    for b, n in enumerate(lens):
+        batch[b, :n] = torch.from_numpy(wav[:n]) * (1 + b)
+    spec, frames = native.native.spectrogram(batch.cuda(), torch.tensor(lens).cuda())
+    assert frames.tolist() == [n // 256 for n in lens]
+    for b, n in enumerate(lens):
+        ref = O.spectrogram(batch[b: b + 1, :n])
+        got = spec[b, :, : n // 256].cpu()
+        assert rel_err(got.numpy(), ref[0].numpy()) < 2e-5, b
+        assert float(spec[b, :, n // 256:].abs().max()) == 0.0 if n // 256 < L // 256 else True
+
+
 def test_api_convert_matches_reference_golden(tmp_path, synthetic_sd):
     """ToneColorConverter.convert end to end (waveform -> spectrogram -> VC -> samples) against
     the real reference's convert() output."""
