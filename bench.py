@@ -302,10 +302,18 @@ def main():
     k_ms = prof["ms"] / max(1, prof["launches"])
     ach_gbs = prof["bytes"] / max(1e-9, prof["ms"] * 1e-3) / 1e9
     ach_tf = prof["flops"] / max(1e-9, prof["ms"] * 1e-3) / 1e12
+    traffic, traffic_note = None, None
+    try:   # dram bytes of the top kernel from the committed ncu --set full capture (profiles/)
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_A_K11D1_ffma2.json")))[0]
+        traffic = (float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])) * 1e6
+        traffic_note = ("ncu dram read+write of one conv1d_f32<11,1,4,2,4> launch at batch 8 (C=128, 440832 steps): "
+                        "algorithmic in+out+residual = 677 MB")
+    except Exception:
+        pass
     roofline = {
         "kernel": "conv1d_f32<EPI_LINEAR> (generator ResBlock1 convs, 72 launches per call)",
         "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
         "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_dev,
         "binding": "fp32 FFMA (dense contraction, SURVEY.md section 8d)",
         "ffma": {"achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FFMA_PEAK_TFLOPS,

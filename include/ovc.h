@@ -142,6 +142,11 @@ OVC_API int ovc_last_launch_count(const ovc_ctx* ctx);
  * since the last reset. */
 OVC_API int ovc_profile_enable(ovc_ctx* ctx, int enable);
 OVC_API int ovc_profile_read(ovc_ctx* ctx, double* ms, int64_t* launches, double* flops, double* bytes);
+/* Per-launch detail of every conv kernel since the last reset (call before ovc_profile_read):
+ * kernel-variant name (16 bytes each), milliseconds, algorithmic FLOPs / bytes, family (1 = generator
+ * ResBlock convs).  Returns the number of entries written (<= max). */
+OVC_API int ovc_profile_detail(ovc_ctx* ctx, int max, char* names, double* ms, double* flops, double* bytes,
+                               int* family);
 
 /* Debug taps (tests only): when enabled, named intermediate tensors of the next call are
  * copied aside; ovc_debug_fetch copies one to host memory.  Names: "enc.pre", "enc.wn",

@@ -17,7 +17,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "ovc_abi_version", "ovc_last_error", "ovc_create", "ovc_destroy", "ovc_load_tensor",
     "ovc_finalize_weights", "ovc_workspace_floats", "ovc_voice_conversion", "ovc_last_launch_count",
-    "ovc_profile_enable", "ovc_profile_read", "ovc_debug_enable", "ovc_debug_fetch",
+    "ovc_profile_enable", "ovc_profile_read", "ovc_profile_detail", "ovc_debug_enable", "ovc_debug_fetch",
     "ovc_spectrogram", "ovc_convert_waveform",
 )
 
@@ -69,6 +69,8 @@ def load_library(path: Optional[str] = None):
     lib.ovc_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.ovc_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ovc_profile_detail.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.ovc_debug_enable.argtypes = [C.c_void_p, C.c_int]
     lib.ovc_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
     lib.ovc_spectrogram.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
@@ -253,6 +255,18 @@ class NativeConverter:
         _check(self.lib, self.lib.ovc_profile_read(self.handle, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)),
                "ovc_profile_read")
         return dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+
+    def profile_detail(self, max_entries: int = 4096):
+        """Per-launch (name, ms, flops, bytes, family) of the conv kernels since the last reset."""
+        names = C.create_string_buffer(16 * max_entries)
+        ms = (C.c_double * max_entries)()
+        fl = (C.c_double * max_entries)()
+        by = (C.c_double * max_entries)()
+        fam = (C.c_int * max_entries)()
+        n = self.lib.ovc_profile_detail(self.handle, max_entries, names, ms, fl, by, fam)
+        _check(self.lib, n, "ovc_profile_detail")
+        raw = names.raw
+        return [(raw[16 * i: 16 * i + 16].split(b"\0")[0].decode(), ms[i], fl[i], by[i], fam[i]) for i in range(n)]
 
     def debug_enable(self, on: bool):
         _check(self.lib, self.lib.ovc_debug_enable(self.handle, 1 if on else 0), "ovc_debug_enable")

@@ -76,6 +76,7 @@ struct ConvLayer {
   size_t b_off = 0;
   int K = 1;           // true taps / channels, for FLOP accounting
   int cout = 0;
+  int out_mul = 1;     // outputs per input step (transposed convs: stride)
 };
 
 struct WNLayers {
@@ -134,6 +135,7 @@ struct ovc_ctx {
   double prof_ms = 0, prof_flops = 0, prof_bytes = 0;
   int64_t prof_launches = 0;
   std::vector<double> ev_flops, ev_bytes;
+  std::vector<int> ev_variant, ev_family;
 
   // debug taps
   bool debug = false;
@@ -354,6 +356,7 @@ static int finalize(ovc_ctx* c) {
           return (kidx >= 0 && kidx < kk) ? w.data[((size_t)ci * cout + co) * kk + kidx] : 0.f;
         },
         [&](int co) { return b->data[co]; }, cout, 2, cout);
+    c->dec_ups[i].out_mul = s;
     ch = cout;
     for (int j = 0; j < 3; ++j) {
       const int K = hp.resblock_kernel_sizes[j];
@@ -512,7 +515,7 @@ struct Run {
   double sum_len;           // sum over batch of generator frames (for FLOP/byte accounting): B*Tmax upper bound
 };
 
-static int launch(Run& r, const ConvLayer& L, ConvArgs a, int t_len, bool profiled = false, double flops = 0,
+static int launch(Run& r, const ConvLayer& L, ConvArgs a, int t_len, bool mrf = false, double flops = 0,
                   double bytes = 0) {
   a.w = r.c->d_w + L.w_off;
   a.n_chunks = L.n_chunks;
@@ -520,11 +523,11 @@ static int launch(Run& r, const ConvLayer& L, ConvArgs a, int t_len, bool profil
   a.tmax = r.Tmax;
   if (a.scale == 0.f) a.scale = 1.f;
   ovc_ctx* c = r.c;
-  const bool prof = profiled && c->prof;
+  const bool prof = c->prof;
   if (prof) {
     if (c->ev_used + 2 > c->ev.size()) {
       const size_t old = c->ev.size();
-      c->ev.resize(old + 256);
+      c->ev.resize(old + 512);
       for (size_t i = old; i < c->ev.size(); ++i) CK(cudaEventCreate(&c->ev[i]));
     }
     CK(cudaEventRecord(c->ev[c->ev_used], r.st));
@@ -534,9 +537,14 @@ static int launch(Run& r, const ConvLayer& L, ConvArgs a, int t_len, bool profil
   if (prof) {
     CK(cudaEventRecord(c->ev[c->ev_used + 1], r.st));
     c->ev_used += 2;
-    c->ev_flops.push_back(flops);
-    c->ev_bytes.push_back(bytes);
+    // algorithmic work of this launch over all B * t_len positions (upper bound for ragged batches)
+    const double units = (double)r.B * t_len;
+    c->ev_flops.push_back(2.0 * L.cout * L.cin * L.K * units * L.out_mul);
+    c->ev_bytes.push_back(4.0 * units * ((double)L.cin + (double)L.cout * L.out_mul));
+    c->ev_variant.push_back(L.variant);
+    c->ev_family.push_back(mrf ? 1 : 0);
   }
+  (void)flops; (void)bytes;
   return OVC_OK;
 }
 
@@ -919,27 +927,49 @@ int ovc_profile_enable(ovc_ctx* c, int enable) {
   c->ev_used = 0;
   c->ev_flops.clear();
   c->ev_bytes.clear();
+  c->ev_variant.clear();
+  c->ev_family.clear();
   return OVC_OK;
 }
 
 int ovc_profile_read(ovc_ctx* c, double* ms, int64_t* launches, double* flops, double* bytes) {
   if (!c) return fail(OVC_ERR_INVALID, "null context");
   double tms = 0, tf = 0, tb = 0;
+  int64_t n = 0;
   for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    if (!c->ev_family[i / 2]) continue;
     float m = 0;
     CK(cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]));
     tms += m;
     tf += c->ev_flops[i / 2];
     tb += c->ev_bytes[i / 2];
+    ++n;
   }
   if (ms) *ms = tms;
-  if (launches) *launches = (int64_t)(c->ev_used / 2);
+  if (launches) *launches = n;
   if (flops) *flops = tf;
   if (bytes) *bytes = tb;
   c->ev_used = 0;
   c->ev_flops.clear();
   c->ev_bytes.clear();
+  c->ev_variant.clear();
+  c->ev_family.clear();
   return OVC_OK;
+}
+
+int ovc_profile_detail(ovc_ctx* c, int max, char* names /* max x 16 */, double* ms, double* flops, double* bytes, int* family) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  int n = 0;
+  for (size_t i = 0; i + 1 < c->ev_used && n < max; i += 2, ++n) {
+    float m = 0;
+    CK(cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]));
+    if (names) { strncpy(names + 16 * n, kInfo[c->ev_variant[i / 2]].name, 15); names[16 * n + 15] = 0; }
+    if (ms) ms[n] = m;
+    if (flops) flops[n] = c->ev_flops[i / 2];
+    if (bytes) bytes[n] = c->ev_bytes[i / 2];
+    if (family) family[n] = c->ev_family[i / 2];
+  }
+  return n;
 }
 
 int ovc_debug_enable(ovc_ctx* c, int enable) {

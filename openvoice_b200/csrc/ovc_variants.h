@@ -3,6 +3,7 @@
 #pragma once
 #include "ovc_conv.cuh"
 
+
 // posterior encoder + flow (time axis = spectrogram frames): 64 rows x 128 frames, 128 threads
 #define OVC_VARIANTS_G0(X)                                  \
   X(ENC_PRE, 1, 1, 2, 2, 8, EPI_LINEAR, 1, 4)               \
@@ -21,12 +22,12 @@
   X(A_K3D3, 3, 3, 4, 2, 8, EPI_LINEAR, 1, 16)               \
   X(A_K3D5, 3, 5, 4, 2, 8, EPI_LINEAR, 1, 16)               \
   X(A_K7D1, 7, 1, 4, 2, 4, EPI_LINEAR, 1, 16)               \
-  X(A_K7D3, 7, 3, 4, 2, 4, EPI_LINEAR, 2, 16)               \
-  X(A_K7D5, 7, 5, 4, 2, 4, EPI_LINEAR, 2, 16)
+  X(A_K7D3, 7, 3, 4, 2, 8, EPI_LINEAR, 2, 16)               \
+  X(A_K7D5, 7, 5, 4, 2, 8, EPI_LINEAR, 2, 16)
 #define OVC_VARIANTS_G2(X)                                  \
   X(A_K11D1, 11, 1, 4, 2, 4, EPI_LINEAR, 1, 16)             \
-  X(A_K11D3, 11, 3, 4, 2, 4, EPI_LINEAR, 3, 16)             \
-  X(A_K11D5, 11, 5, 4, 2, 4, EPI_LINEAR, 4, 16)
+  X(A_K11D3, 11, 3, 4, 2, 8, EPI_LINEAR, 3, 16)             \
+  X(A_K11D5, 11, 5, 4, 2, 8, EPI_LINEAR, 4, 16)
 
 // generator, class B: 64 rows x 256 samples (C = 64)
 #define OVC_VARIANTS_G3(X)                                  \

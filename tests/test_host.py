@@ -158,7 +158,7 @@ else:
     assert out is None
 dist.barrier()
 dist.destroy_process_group()
-print("worker", rank, "ok")
+sys.stdout.write(f"worker-{rank}-ok\n"); sys.stdout.flush()
 """
 
 
@@ -166,9 +166,13 @@ def test_multi_gpu_driver_under_gloo_world2(tmp_path):
     """The N>1 path (checkpoint broadcast, LPT sharding, waveform gather) with 2 CPU processes."""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
+    import socket
+    with socket.socket() as sk:          # a free port: back-to-back runs must not collide on TIME_WAIT
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert "worker 0 ok" in r.stdout and "worker 1 ok" in r.stdout
+    assert "worker-0-ok" in r.stdout and "worker-1-ok" in r.stdout
