@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU reference arm")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips in the cpu_baseline sample of the native arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("OVC_PRECISION", "fp32"), choices=["fp32", "tf32x3"],
+                    help="generator ResBlock conv arithmetic: fp32 FFMA2 (default) or 3xTF32 tensor cores")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -238,6 +240,7 @@ def main():
         conv = ToneColorConverter(cfg, device=dev, enable_watermark=False)
     conv.model.load_state_dict(sd)
     del sd
+    conv.model.native.set_precision(args.precision)
 
     B, secs = args.batch, args.secs
     waves = [synth_wave(rank * B + i, secs) for i in range(B)]

@@ -132,6 +132,13 @@ OVC_API int ovc_convert_waveform(ovc_ctx* ctx, const float* wav, const int64_t* 
                                  const float* g_src, const float* g_tgt, const float* noise, uint64_t seed,
                                  float tau, float* o_hat, int64_t* frames, void* stream);
 
+/* Arithmetic of the generator's ResBlock convolutions (90 % of the FLOPs):
+ *   0 (default)  fp32 FFMA2 on the CUDA cores
+ *   1            split-precision 3xTF32 on the 5th-gen tensor cores (tcgen05 + TMEM): every product is
+ *                a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with tf32-exact high parts, fp32 accumulation --
+ *                fp32-grade (~1e-6) error, same parity gate as mode 0                               */
+OVC_API int ovc_set_precision(ovc_ctx* ctx, int mode);
+
 /* Number of kernels the last ovc_voice_conversion / ovc_convert_waveform call launched. */
 OVC_API int ovc_last_launch_count(const ovc_ctx* ctx);
 

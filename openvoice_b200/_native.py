@@ -18,7 +18,7 @@ EXPORTS = (
     "ovc_abi_version", "ovc_last_error", "ovc_create", "ovc_destroy", "ovc_load_tensor",
     "ovc_finalize_weights", "ovc_workspace_floats", "ovc_voice_conversion", "ovc_last_launch_count",
     "ovc_profile_enable", "ovc_profile_read", "ovc_profile_detail", "ovc_debug_enable", "ovc_debug_fetch",
-    "ovc_spectrogram", "ovc_convert_waveform",
+    "ovc_spectrogram", "ovc_convert_waveform", "ovc_set_precision",
 )
 
 
@@ -66,6 +66,7 @@ def load_library(path: Optional[str] = None):
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float,
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ovc_last_launch_count.argtypes = [C.c_void_p]
+    lib.ovc_set_precision.argtypes = [C.c_void_p, C.c_int]
     lib.ovc_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.ovc_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -171,6 +172,12 @@ class NativeConverter:
     def finalize(self):
         _check(self.lib, self.lib.ovc_finalize_weights(self.handle), "ovc_finalize_weights")
         self.finalized = True
+
+    def set_precision(self, mode: str):
+        """'fp32' (CUDA-core FFMA2, default) or 'tf32x3' (split-precision tensor-core ResBlock convs)."""
+        m = {"fp32": 0, "tf32x3": 1}[mode]
+        _check(self.lib, self.lib.ovc_set_precision(self.handle, m), "ovc_set_precision")
+        self.precision = mode
 
     # ---- hot path --------------------------------------------------------------------------
     def voice_conversion(self, spec, lengths, g_src, g_tgt, noise=None, tau: float = 0.3, seed: int = 0,

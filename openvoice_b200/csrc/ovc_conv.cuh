@@ -337,7 +337,7 @@ __device__ __forceinline__ void stage_x_activate(float* xs, float slope) {
 // ---------------------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) conv1d_f32(const ConvArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* wsm = reinterpret_cast<float*>(smem_raw + 16);
   float* xsm = wsm + 2 * C::W_STAGE;

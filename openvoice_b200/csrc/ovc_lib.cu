@@ -14,6 +14,7 @@
 
 #include "../../include/ovc.h"
 #include "ovc_small.cuh"
+#include "ovc_tcconv.cuh"
 #include "ovc_variants.h"
 
 namespace ovc {
@@ -79,6 +80,12 @@ struct ConvLayer {
   int out_mul = 1;     // outputs per input step (transposed convs: stride)
 };
 
+// one ResBlock conv as the tensor-core kernel sees it (pre-split hi/lo weights in operand layout)
+struct TcLayer {
+  size_t w_off = 0;   // float offset into the tc weight arena
+  int C = 0, K = 0, DIL = 1, TN = 0;
+};
+
 struct WNLayers {
   std::vector<ConvLayer> in, rs;
 };
@@ -112,6 +119,10 @@ struct ovc_ctx {
   WNLayers flow_wn[4];
   ConvLayer dec_pre, dec_ups[4];
   ConvLayer rb_c1[12][3], rb_c2[12][3];
+  TcLayer tc_c1[12][3], tc_c2[12][3];
+  float* d_tcw = nullptr;      // tensor-core weight arena (hi/lo split)
+  std::vector<float> h_tcw;
+  int precision = 0;           // 0: fp32 FFMA everywhere; 1: 3xTF32 tcgen05 for the generator ResBlock convs
   size_t post_w_off = 0;
   // cond mat-vec
   size_t cond_w_off = 0, cond_b_off = 0;
@@ -282,6 +293,7 @@ static int finalize(ovc_ctx* c) {
   const int H = 192, S = hp.spec_channels, G = hp.gin_channels;
   std::string miss;
   c->h_w.clear();
+  c->h_tcw.clear();
 #define NEED(ptr, key)                                                                     \
   const HostTensor* ptr = find(c, key);                                                    \
   if (!ptr) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing", std::string(key).c_str())
@@ -372,6 +384,32 @@ static int finalize(ovc_ctx* c) {
                                   [&](int r, int ci, int k) { return rw.data[((size_t)r * ch + ci) * K + k]; },
                                   [&](int r) { return rbias->data[r]; }, ch, K, ch);
           (which ? c->rb_c2 : c->rb_c1)[rbi][d] = L;
+          {  // tensor-core copy: [n_tile][C/8][K][hi|lo][k chunk][TN][4], tf32-exact high part + fp32 remainder
+            TcLayer T;
+            T.C = ch; T.K = K; T.DIL = dil; T.TN = ch < 128 ? ch : 128;
+            T.w_off = round_up(c->h_tcw.size(), 64);
+            const int slot = 2 * 2 * T.TN * 4;
+            c->h_tcw.resize(T.w_off + (size_t)(ch / T.TN) * (ch / 8) * K * slot, 0.f);
+            float* dst = c->h_tcw.data() + T.w_off;
+            for (int nt = 0; nt < ch / T.TN; ++nt)
+              for (int k8 = 0; k8 < ch / 8; ++k8)
+                for (int tap = 0; tap < K; ++tap) {
+                  float* sl = dst + (((size_t)nt * (ch / 8) + k8) * K + tap) * slot;
+                  for (int kc = 0; kc < 2; ++kc)
+                    for (int n = 0; n < T.TN; ++n)
+                      for (int e = 0; e < 4; ++e) {
+                        const float w = rw.data[((size_t)(nt * T.TN + n) * ch + k8 * 8 + kc * 4 + e) * K + tap];
+                        uint32_t bits;
+                        memcpy(&bits, &w, 4);
+                        bits &= 0xFFFFE000u;
+                        float hi;
+                        memcpy(&hi, &bits, 4);
+                        sl[(kc * T.TN + n) * 4 + e] = hi;
+                        sl[2 * T.TN * 4 + (kc * T.TN + n) * 4 + e] = w - hi;
+                      }
+                }
+            (which ? c->tc_c2 : c->tc_c1)[rbi][d] = T;
+          }
         }
       }
     }
@@ -444,6 +482,14 @@ static int finalize(ovc_ctx* c) {
   c->w_floats = c->h_w.size();
   CK(cudaMalloc(&c->d_w, c->w_floats * sizeof(float)));
   CK(cudaMemcpy(c->d_w, c->h_w.data(), c->w_floats * sizeof(float), cudaMemcpyHostToDevice));
+  if (c->d_tcw) { cudaFree(c->d_tcw); c->d_tcw = nullptr; }
+  CK(cudaMalloc(&c->d_tcw, c->h_tcw.size() * sizeof(float)));
+  CK(cudaMemcpy(c->d_tcw, c->h_tcw.data(), c->h_tcw.size() * sizeof(float), cudaMemcpyHostToDevice));
+  c->h_tcw.clear();
+  c->h_tcw.shrink_to_fit();
+  CK(cudaFuncSetAttribute(tcconv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<128>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<64>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<32>::SMEM_BYTES));
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
   CK(cudaMalloc(&c->d_cond_wrow, wrow.size() * sizeof(int)));
@@ -476,7 +522,7 @@ static int finalize(ovc_ctx* c) {
 // ---------------------------------------------------------------------------------------------
 struct WsLayout {
   int P;   // frame pitch (multiple of 4)
-  size_t cond, x, skip, acts, z, dpre, bufA, bufB, bufC, bufD, spec, frames, total;
+  size_t cond, x, skip, acts, z, dpre, bufA, bufB, bufC, bufD, bufE, bufF, spec, frames, total;
 };
 static WsLayout ws_layout(const ovc_ctx* c, int B, int Tmax) {
   WsLayout L;
@@ -494,6 +540,8 @@ static WsLayout ws_layout(const ovc_ctx* c, int B, int Tmax) {
   L.bufB = take(big);
   L.bufC = take(big);
   L.bufD = take(big);
+  L.bufE = c->precision ? take(big) : 0;
+  L.bufF = c->precision ? take(big) : 0;
   L.spec = take((size_t)B * c->hp.spec_channels * L.P);
   L.frames = take((size_t)2 * B + 4);   // B int64
   L.total = o;
@@ -563,6 +611,69 @@ static int tap(Run& r, const char* name, const float* src, int C, int T, int pit
   return OVC_OK;
 }
 
+
+// profiling bracket shared by the non-conv1d_f32 launches
+static int prof_begin(Run& r) {
+  ovc_ctx* c = r.c;
+  if (!c->prof) return OVC_OK;
+  if (c->ev_used + 2 > c->ev.size()) {
+    const size_t old = c->ev.size();
+    c->ev.resize(old + 512);
+    for (size_t i = old; i < c->ev.size(); ++i) CK(cudaEventCreate(&c->ev[i]));
+  }
+  CK(cudaEventRecord(c->ev[c->ev_used], r.st));
+  return OVC_OK;
+}
+static int prof_end(Run& r, int variant, int family, double flops, double bytes) {
+  ovc_ctx* c = r.c;
+  if (!c->prof) return OVC_OK;
+  CK(cudaEventRecord(c->ev[c->ev_used + 1], r.st));
+  c->ev_used += 2;
+  c->ev_flops.push_back(flops);
+  c->ev_bytes.push_back(bytes);
+  c->ev_variant.push_back(variant);
+  c->ev_family.push_back(family);
+  return OVC_OK;
+}
+enum { V_TC128 = -1, V_TC64 = -2, V_TC32 = -3, V_TRANSPOSE = -4 };
+static const char* variant_name(int v) {
+  if (v >= 0) return kInfo[v].name;
+  return v == V_TC128 ? "TC3_N128" : v == V_TC64 ? "TC3_N64" : v == V_TC32 ? "TC3_N32" : "TRANSPOSE";
+}
+
+// one generator ResBlock conv on the tensor cores (3xTF32), channels-last in/out
+static int launch_tc(Run& r, const TcLayer& T, const float* bias, const float* x, float* y, const float* res, int t_len,
+                     int mul, float slope, float scale, int accumulate) {
+  TcConvArgs a{};
+  a.x = x; a.x_bs = (long long)T.C * r.P * mul;
+  a.w = r.c->d_tcw + T.w_off;
+  a.bias = bias;
+  a.y = y; a.y_bs = a.x_bs;
+  a.r = res;
+  a.lens = r.glens; a.tmax = r.Tmax; a.mul = mul;
+  a.C = T.C; a.K = T.K; a.DIL = T.DIL;
+  a.slope = slope; a.scale = scale; a.accumulate = accumulate;
+  dim3 grid((t_len + TC_MT * 128 - 1) / (TC_MT * 128), T.C / T.TN, r.B);
+  TRY(prof_begin(r));
+  if (T.TN == 128) tcconv_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, r.st>>>(a);
+  else if (T.TN == 64) tcconv_kernel<64><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, r.st>>>(a);
+  else tcconv_kernel<32><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, r.st>>>(a);
+  CK(cudaGetLastError());
+  r.c->launches++;
+  const double units = (double)r.B * t_len;
+  TRY(prof_end(r, T.TN == 128 ? V_TC128 : T.TN == 64 ? V_TC64 : V_TC32, 1, 2.0 * T.C * T.C * T.K * units, 8.0 * T.C * units));
+  return OVC_OK;
+}
+
+static int launch_transpose(Run& r, const float* src, float* dst, int rows, int cols) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, r.B);
+  TRY(prof_begin(r));
+  transpose_kernel<<<grid, 256, 0, r.st>>>(src, dst, rows, cols, (long long)rows * cols);
+  CK(cudaGetLastError());
+  r.c->launches++;
+  TRY(prof_end(r, V_TRANSPOSE, 0, 0.0, 8.0 * rows * cols * r.B));
+  return OVC_OK;
+}
 
 // one WN stack (modules.py:185-210): x <- in place, skip <- output
 static int run_wn(Run& r, const WNLayers& wn, float* x, float* skip, float* acts, const float* cond, int cond_bs) {
@@ -739,6 +850,24 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
     // MRF: xs = sum_j ResBlock1_j(x) / 3 (models.py:280-286; ResBlock1 = modules.py:296-309)
     const long long bsC = (long long)cout * pitch_out;
     const int Tlen = Tmax * up_out;
+    float* stage_out = bufD;
+    if (c->precision == 1) {
+      // tensor-core path: channels-last [t][C] inside the MRF, transposed at its boundary
+      float* bufE = ws + W.bufE;
+      float* bufF = ws + W.bufF;
+      TRY(launch_transpose(r, bufA, bufE, cout, pitch_out));
+      for (int j = 0; j < 3; ++j)
+        for (int d = 0; d < 3; ++d) {
+          const float* xin = d == 0 ? bufE : bufB;
+          TRY(launch_tc(r, c->tc_c1[i * 3 + j][d], c->d_w + c->rb_c1[i * 3 + j][d].b_off, xin, bufC, nullptr, Tlen, up_out,
+                        0.1f, 1.f, 0));
+          float* yout = d < 2 ? bufB : bufD;
+          TRY(launch_tc(r, c->tc_c2[i * 3 + j][d], c->d_w + c->rb_c2[i * 3 + j][d].b_off, bufC, yout, xin, Tlen, up_out, 0.1f,
+                        (d == 2 && j == 2) ? 1.0f / 3.0f : 1.f, (d == 2 && j > 0) ? 1 : 0));
+        }
+      TRY(launch_transpose(r, bufD, bufF, pitch_out, cout));
+      stage_out = bufF;
+    } else {
     for (int j = 0; j < 3; ++j) {
       const int K = c->hp.resblock_kernel_sizes[j];
       for (int d = 0; d < 3; ++d) {
@@ -768,16 +897,17 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
         TRY(launch(r, c->rb_c2[i * 3 + j][d], b, Tlen, true, fl, by));
       }
     }
+    }
     char nm[32]; snprintf(nm, sizeof nm, "dec.stage%d", i);
-    TRY(tap(r, nm, bufD, cout, Tlen, pitch_out));
-    stage_in = bufD;
+    TRY(tap(r, nm, stage_out, cout, Tlen, pitch_out));
+    stage_in = stage_out;
     cin = cout; up = up_out;
   }
   // leaky_relu(0.01) + conv_post + tanh (models.py:287-289)
   {
     const int y_len = Tmax * up;   // 256 * Tmax
     dim3 grid((y_len / 4 + 255) / 256, B);
-    conv_post_kernel<32><<<grid, 256, 0, st>>>(bufD, 32LL * P * up, P * up, c->d_w + c->post_w_off, o_hat,
+    conv_post_kernel<32><<<grid, 256, 0, st>>>(stage_in, 32LL * P * up, P * up, c->d_w + c->post_w_off, o_hat,
                                               (long long)y_len, y_len, r.glens, Tmax, up);
     CK(cudaGetLastError());
     c->launches++;
@@ -828,6 +958,7 @@ void ovc_destroy(ovc_ctx* c) {
   if (c->d_ws) cudaFree(c->d_ws);
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
+  if (c->d_tcw) cudaFree(c->d_tcw);
   if (c->d_tw) cudaFree(c->d_tw);
   if (c->d_win) cudaFree(c->d_win);
   for (auto& e : c->ev) cudaEventDestroy(e);
@@ -919,6 +1050,13 @@ int ovc_convert_waveform(ovc_ctx* c, const float* wav, const int64_t* wav_length
   return rc;
 }
 
+int ovc_set_precision(ovc_ctx* c, int mode) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  if (mode != 0 && mode != 1) return fail(OVC_ERR_INVALID, "precision mode must be 0 (fp32 FFMA) or 1 (3xTF32 tensor cores)");
+  c->precision = mode;
+  return OVC_OK;
+}
+
 int ovc_last_launch_count(const ovc_ctx* c) { return c ? c->launches : 0; }
 
 int ovc_profile_enable(ovc_ctx* c, int enable) {
@@ -963,7 +1101,7 @@ int ovc_profile_detail(ovc_ctx* c, int max, char* names /* max x 16 */, double* 
   for (size_t i = 0; i + 1 < c->ev_used && n < max; i += 2, ++n) {
     float m = 0;
     CK(cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]));
-    if (names) { strncpy(names + 16 * n, kInfo[c->ev_variant[i / 2]].name, 15); names[16 * n + 15] = 0; }
+    if (names) { strncpy(names + 16 * n, variant_name(c->ev_variant[i / 2]), 15); names[16 * n + 15] = 0; }
     if (ms) ms[n] = m;
     if (flops) flops[n] = c->ev_flops[i / 2];
     if (bytes) bytes[n] = c->ev_bytes[i / 2];

@@ -1,0 +1,228 @@
+// ovc_tcconv.cuh -- split-precision (3xTF32) tensor-core Conv1d for the generator's ResBlock convs.
+//
+//   Y[t, n] = (bias[n] + sum_{tap, c} W[n, c, tap] * lrelu(X[t + (tap - (K-1)/2) * DIL, c]) [+ R[t, n]] [+ Y_old[t, n]]) * scale
+//
+// Channels-last activations X[b][t][C] (time-major rows).  Every product is evaluated as
+// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with tf32-exact high parts and fp32 remainders (error ~1e-6,
+// i.e. fp32-grade; tools/tc_gemm_test.cu), accumulated in fp32 in TMEM by tcgen05.mma.kind::tf32.
+//
+// One CTA = 512 time steps (4 MMA tiles of M=128) x TN output channels (TMEM: 4*TN columns).
+// K-major, no-swizzle operand tiles (see ovc_tc.cuh): a convolution tap is a 16-byte-per-row shift
+// of the A descriptor's start address, so all taps (any dilation) read ONE staged halo tile.
+// Warp roles (192 threads):
+//   warp 0      : TMA bulk copies of pre-split, pre-laid-out weight slots [tap][hi|lo] into an 8-slot ring
+//   warp 1      : single-thread tcgen05.mma issue; tcgen05.commit releases ring slots / A buffers
+//   warps 2..5  : A producers -- global (16 B, zero-filled past the utterance) -> lrelu -> hi/lo split
+//                 -> shared (2 buffers, 8 input channels each); afterwards the epilogue warps:
+//                 tcgen05.ld -> bias / residual / MRF accumulate / scale -> global
+#pragma once
+#include "ovc_conv.cuh"
+#include "ovc_tc.cuh"
+
+namespace ovc {
+
+struct TcConvArgs {
+  const float* x; long long x_bs;     // [B][Lpitch][C]
+  const float* w;                      // packed [n_tiles][C/8][K][2 (hi|lo)][2 (k chunk)][TN][4]
+  const float* bias;                   // [C]
+  float* y; long long y_bs;            // [B][Lpitch][C]
+  const float* r;                      // residual, same geometry as y (nullable)
+  const long long* lens; int tmax; int mul;   // valid steps = min(tmax, lens[b]) * mul   (lens NULL -> tmax)
+  int C; int K; int DIL;
+  float slope; float scale; int accumulate;
+};
+
+constexpr int TC_MT = 4;                 // MMA tiles (of 128 steps) per CTA
+constexpr int TC_ROWS = 576;             // staged rows per buffer (512 + 2*25 halo, padded)
+constexpr int TC_SLOTS = 8;              // weight ring depth
+constexpr int TC_THREADS = 192;
+
+template <int TN>
+struct TcCfg {
+  static constexpr int A_BUF_FLOATS = 2 * 2 * TC_ROWS * 4;       // [hi|lo][k chunk][row][4]
+  static constexpr int B_SLOT_FLOATS = 2 * 2 * TN * 4;           // [hi|lo][k chunk][n][4]
+  static constexpr size_t SMEM_BYTES = 256 + sizeof(float) * (2 * A_BUF_FLOATS + TC_SLOTS * B_SLOT_FLOATS);
+  static constexpr uint32_t TMEM_COLS = TC_MT * TN;              // 128 / 256 / 512
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int TN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs a) {
+  using Cfg = TcCfg<TN>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);   // [0..1] a_full, [2..3] a_empty, [4..11] b_full, [12..19] b_empty, [20] acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 21 * 8);
+  float* abuf = reinterpret_cast<float*>(smem_raw + 256);
+  float* bring = abuf + 2 * Cfg::A_BUF_FLOATS;
+  uint64_t* a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 12, *acc_full = bars + 20;
+
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * (TC_MT * 128);
+  const int n0 = blockIdx.y * TN;
+  const int lim = (a.lens ? (int)min((long long)a.tmax, a.lens[b]) : a.tmax) * a.mul;
+  if (t0 >= lim) return;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = (a.K - 1) / 2 * a.DIL;
+  const int rows = TC_MT * 128 + 2 * H;
+  const int nk8 = a.C / 8;
+
+  if (tid == 0) {
+    mbar_init(&a_full[0], 128); mbar_init(&a_full[1], 128);
+    mbar_init(&a_empty[0], 1); mbar_init(&a_empty[1], 1);
+    for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight producer (TMA bulk)
+    if (lane == 0) {
+      const float* wt = a.w + (size_t)blockIdx.y * nk8 * a.K * Cfg::B_SLOT_FLOATS;
+      constexpr uint32_t BYTES = Cfg::B_SLOT_FLOATS * sizeof(float);
+      int it = 0;
+      for (int k8 = 0; k8 < nk8; ++k8)
+        for (int tap = 0; tap < a.K; ++tap, ++it) {
+          const int slot = it % TC_SLOTS, round = it / TC_SLOTS;
+          mbar_wait(&b_empty[slot], (round & 1) ^ 1);
+          mbar_expect_tx(&b_full[slot], BYTES);
+          tma_bulk_g2s(bring + slot * Cfg::B_SLOT_FLOATS, wt + (size_t)it * Cfg::B_SLOT_FLOATS, BYTES, &b_full[slot]);
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(128, TN);
+      constexpr uint32_t LBO_A = TC_ROWS * 16, LBO_B = TN * 16, SBO = 128;
+      constexpr uint32_t A_LO_OFF = 2 * TC_ROWS * 16;        // bytes from hi to lo inside an A buffer
+      constexpr uint32_t B_LO_OFF = 2 * TN * 16;
+      int it = 0;
+      for (int k8 = 0; k8 < nk8; ++k8) {
+        const int buf = k8 & 1;
+        mbar_wait(&a_full[buf], (k8 >> 1) & 1);
+        tc::fence_after();
+        const uint32_t a_base = tc::smem_addr(abuf + buf * Cfg::A_BUF_FLOATS);
+        for (int tap = 0; tap < a.K; ++tap, ++it) {
+          const int slot = it % TC_SLOTS, round = it / TC_SLOTS;
+          mbar_wait(&b_full[slot], round & 1);
+          tc::fence_after();
+          const uint32_t b_base = tc::smem_addr(bring + slot * Cfg::B_SLOT_FLOATS);
+          const uint64_t bd_hi = tc::make_desc(b_base, LBO_B, SBO);
+          const uint64_t bd_lo = tc::make_desc(b_base + B_LO_OFF, LBO_B, SBO);
+          const bool first = (k8 == 0 && tap == 0);
+#pragma unroll
+          for (int mt = 0; mt < TC_MT; ++mt) {
+            // output step (t0 + mt*128 + i) reads staged row (mt*128 + i + tap*DIL): the halo tile starts at t0 - H
+            const uint32_t a_off = (uint32_t)(mt * 128 + tap * a.DIL) * 16;
+            const uint64_t ad_hi = tc::make_desc(a_base + a_off, LBO_A, SBO);
+            const uint64_t ad_lo = tc::make_desc(a_base + A_LO_OFF + a_off, LBO_A, SBO);
+            const uint32_t d = tmem_d + mt * TN;
+            tc::mma_tf32(d, ad_hi, bd_hi, idesc, !first);
+            tc::mma_tf32(d, ad_lo, bd_hi, idesc, true);
+            tc::mma_tf32(d, ad_hi, bd_lo, idesc, true);
+          }
+          tc::mma_commit(&b_empty[slot]);       // slot reusable once these MMAs have read it
+        }
+        tc::mma_commit(&a_empty[buf]);
+      }
+      tc::mma_commit(acc_full);
+    }
+  } else {
+    // ------------------------------------------------------------ A producers, then epilogue
+    const int pt = tid - 64;                                   // 0..127
+    const float* xb = a.x + (size_t)b * a.x_bs;
+    const int items = rows * 2;                                // (row, 16-byte half of the 8 channels)
+    for (int k8 = 0; k8 < nk8; ++k8) {
+      const int buf = k8 & 1;
+      mbar_wait(&a_empty[buf], ((k8 >> 1) & 1) ^ 1);
+      float* ah = abuf + buf * Cfg::A_BUF_FLOATS;
+      float* al = ah + 2 * TC_ROWS * 4;
+      for (int i = pt; i < items; i += 128) {
+        const int row = i >> 1, kc = i & 1;
+        const int t = t0 - H + row;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < lim) v = *reinterpret_cast<const float4*>(xb + (size_t)t * a.C + k8 * 8 + kc * 4);
+        v.x = lrelu(v.x, a.slope); v.y = lrelu(v.y, a.slope); v.z = lrelu(v.z, a.slope); v.w = lrelu(v.w, a.slope);
+        float4 hi, lo;
+        tc::split_tf32(v.x, hi.x, lo.x); tc::split_tf32(v.y, hi.y, lo.y);
+        tc::split_tf32(v.z, hi.z, lo.z); tc::split_tf32(v.w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(ah + (kc * TC_ROWS + row) * 4) = hi;
+        *reinterpret_cast<float4*>(al + (kc * TC_ROWS + row) * 4) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async) proxy
+      mbar_arrive(&a_full[buf]);
+    }
+    // epilogue: warp w may read TMEM lanes [32*(w%4), +32)
+    mbar_wait(acc_full, 0);
+    tc::fence_after();
+    const int lane_base = (warp & 3) * 32;
+    float* yb = a.y + (size_t)b * a.y_bs;
+    const float* rb = a.r ? a.r + (size_t)b * a.y_bs : nullptr;
+#pragma unroll 1
+    for (int mt = 0; mt < TC_MT; ++mt) {
+      const int t = t0 + mt * 128 + lane_base + lane;
+      const bool ok = t < lim;
+      float* yp = yb + (size_t)t * a.C + n0;
+      const float* rp = rb ? rb + (size_t)t * a.C + n0 : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 8) {
+        float v[8];
+        tc::tmem_ld8(tmem_d + ((uint32_t)lane_base << 16) + mt * TN + c0, v);
+        if (ok) {
+          const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n0 + c0);
+          const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          if (rp) {
+            const float4 r0 = *reinterpret_cast<const float4*>(rp + c0), r1 = *reinterpret_cast<const float4*>(rp + c0 + 4);
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+          }
+          if (a.accumulate) {
+            const float4 y0 = *reinterpret_cast<const float4*>(yp + c0), y1 = *reinterpret_cast<const float4*>(yp + c0 + 4);
+            v[0] = y0.x + v[0]; v[1] = y0.y + v[1]; v[2] = y0.z + v[2]; v[3] = y0.w + v[3];
+            v[4] = y1.x + v[4]; v[5] = y1.y + v[5]; v[6] = y1.z + v[6]; v[7] = y1.w + v[7];
+          }
+          if (a.scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= a.scale;
+          }
+          *reinterpret_cast<float4*>(yp + c0) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(yp + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+}
+
+// [B][C][pitch] <-> [B][pitch][C] tiled transpose (32x32 through shared memory)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows,
+                                                        int cols, long long bs) {
+  __shared__ float tile[32][33];
+  const float* s = src + (size_t)blockIdx.z * bs;
+  float* d = dst + (size_t)blockIdx.z * bs;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? s[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) d[(size_t)c * rows + r] = tile[tx][i];
+  }
+}
+
+}  // namespace ovc

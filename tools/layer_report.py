@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--secs", type=float, default=10.0)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3"])
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -36,6 +37,7 @@ def main():
     wlen = torch.full((B,), L, dtype=torch.int64, device="cuda")
     g = 0.1 * torch.randn(B, 256, generator=torch.Generator().manual_seed(1)).cuda()
     nat = conv.model.native
+    nat.set_precision(args.precision)
     for _ in range(2):
         nat.convert_waveform(wav, wlen, g, g, tau=0.3, seed=1)
     torch.cuda.synchronize()
