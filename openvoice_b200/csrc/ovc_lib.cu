@@ -82,8 +82,9 @@ struct ConvLayer {
 
 // one ResBlock conv as the tensor-core kernel sees it (pre-split hi/lo weights in operand layout)
 struct TcLayer {
-  size_t w_off = 0;   // float offset into the tc weight arena
-  int C = 0, K = 0, DIL = 1, TN = 0;
+  size_t w_off = 0;   // float offsets into the tc weight arena
+  size_t b_off = 0;
+  int Cin = 0, Ntot = 0, K = 0, DIL = 1, TN = 0;
 };
 
 struct WNLayers {
@@ -119,7 +120,7 @@ struct ovc_ctx {
   WNLayers flow_wn[4];
   ConvLayer dec_pre, dec_ups[4];
   ConvLayer rb_c1[12][3], rb_c2[12][3];
-  TcLayer tc_c1[12][3], tc_c2[12][3];
+  TcLayer tc_c1[12][3], tc_c2[12][3], tc_ups[4];
   float* d_tcw = nullptr;      // tensor-core weight arena (hi/lo split)
   std::vector<float> h_tcw;
   int precision = 0;           // 0: fp32 FFMA everywhere; 1: 3xTF32 tcgen05 for the generator ResBlock convs
@@ -288,6 +289,39 @@ static int pack_wn(ovc_ctx* c, const std::string& prefix, int n_layers, WNLayers
   return 0;
 }
 
+// tensor-core copy of a conv: [n_tile][Cin/8][K][hi|lo][k chunk][TN][4], tf32-exact high part + fp32
+// remainder, laid out exactly as the kernel's shared-memory operand slots (one TMA bulk copy per slot)
+template <class WF, class BF>
+static TcLayer pack_tc(ovc_ctx* c, int Ntot, int Cin, int K, int DIL, WF wfun, BF bfun) {
+  TcLayer T;
+  T.Cin = Cin; T.Ntot = Ntot; T.K = K; T.DIL = DIL; T.TN = Ntot < 128 ? Ntot : 128;
+  T.w_off = round_up(c->h_tcw.size(), 64);
+  const int slot = 2 * 2 * T.TN * 4;
+  c->h_tcw.resize(T.w_off + (size_t)(Ntot / T.TN) * (Cin / 8) * K * slot, 0.f);
+  float* dst = c->h_tcw.data() + T.w_off;
+  for (int nt = 0; nt < Ntot / T.TN; ++nt)
+    for (int k8 = 0; k8 < Cin / 8; ++k8)
+      for (int tap = 0; tap < K; ++tap) {
+        float* sl = dst + (((size_t)nt * (Cin / 8) + k8) * K + tap) * slot;
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < T.TN; ++n)
+            for (int e = 0; e < 4; ++e) {
+              const float w = wfun(nt * T.TN + n, k8 * 8 + kc * 4 + e, tap);
+              uint32_t bits;
+              memcpy(&bits, &w, 4);
+              bits &= 0xFFFFE000u;
+              float hi;
+              memcpy(&hi, &bits, 4);
+              sl[(kc * T.TN + n) * 4 + e] = hi;
+              sl[2 * T.TN * 4 + (kc * T.TN + n) * 4 + e] = w - hi;
+            }
+      }
+  T.b_off = round_up(c->h_tcw.size(), 64);
+  c->h_tcw.resize(T.b_off + Ntot, 0.f);
+  for (int n = 0; n < Ntot; ++n) c->h_tcw[T.b_off + n] = bfun(n);
+  return T;
+}
+
 static int finalize(ovc_ctx* c) {
   const ovc_hparams& hp = c->hp;
   const int H = 192, S = hp.spec_channels, G = hp.gin_channels;
@@ -369,6 +403,15 @@ static int finalize(ovc_ctx* c) {
         },
         [&](int co) { return b->data[co]; }, cout, 2, cout);
     c->dec_ups[i].out_mul = s;
+    // tensor-core form: channels-last, row = ph * cout + co, so input step n yields the s output rows s*n .. s*n+s-1
+    c->tc_ups[i] = pack_tc(
+        c, s * cout, cin, 3, 1,
+        [&](int row, int ci, int tap) {
+          const int ph = row / cout, co = row % cout;
+          const int kidx = s * (1 - tap) + ph + pad;
+          return (kidx >= 0 && kidx < kk) ? w.data[((size_t)ci * cout + co) * kk + kidx] : 0.f;
+        },
+        [&](int row) { return b->data[row % cout]; });
     ch = cout;
     for (int j = 0; j < 3; ++j) {
       const int K = hp.resblock_kernel_sizes[j];
@@ -384,32 +427,9 @@ static int finalize(ovc_ctx* c) {
                                   [&](int r, int ci, int k) { return rw.data[((size_t)r * ch + ci) * K + k]; },
                                   [&](int r) { return rbias->data[r]; }, ch, K, ch);
           (which ? c->rb_c2 : c->rb_c1)[rbi][d] = L;
-          {  // tensor-core copy: [n_tile][C/8][K][hi|lo][k chunk][TN][4], tf32-exact high part + fp32 remainder
-            TcLayer T;
-            T.C = ch; T.K = K; T.DIL = dil; T.TN = ch < 128 ? ch : 128;
-            T.w_off = round_up(c->h_tcw.size(), 64);
-            const int slot = 2 * 2 * T.TN * 4;
-            c->h_tcw.resize(T.w_off + (size_t)(ch / T.TN) * (ch / 8) * K * slot, 0.f);
-            float* dst = c->h_tcw.data() + T.w_off;
-            for (int nt = 0; nt < ch / T.TN; ++nt)
-              for (int k8 = 0; k8 < ch / 8; ++k8)
-                for (int tap = 0; tap < K; ++tap) {
-                  float* sl = dst + (((size_t)nt * (ch / 8) + k8) * K + tap) * slot;
-                  for (int kc = 0; kc < 2; ++kc)
-                    for (int n = 0; n < T.TN; ++n)
-                      for (int e = 0; e < 4; ++e) {
-                        const float w = rw.data[((size_t)(nt * T.TN + n) * ch + k8 * 8 + kc * 4 + e) * K + tap];
-                        uint32_t bits;
-                        memcpy(&bits, &w, 4);
-                        bits &= 0xFFFFE000u;
-                        float hi;
-                        memcpy(&hi, &bits, 4);
-                        sl[(kc * T.TN + n) * 4 + e] = hi;
-                        sl[2 * T.TN * 4 + (kc * T.TN + n) * 4 + e] = w - hi;
-                      }
-                }
-            (which ? c->tc_c2 : c->tc_c1)[rbi][d] = T;
-          }
+          (which ? c->tc_c2 : c->tc_c1)[rbi][d] =
+              pack_tc(c, ch, ch, K, dil, [&](int r, int ci, int k) { return rw.data[((size_t)r * ch + ci) * K + k]; },
+                      [&](int r) { return rbias->data[r]; });
         }
       }
     }
@@ -641,19 +661,20 @@ static const char* variant_name(int v) {
   return v == V_TC128 ? "TC3_N128" : v == V_TC64 ? "TC3_N64" : v == V_TC32 ? "TC3_N32" : "TRANSPOSE";
 }
 
-// one generator ResBlock conv on the tensor cores (3xTF32), channels-last in/out
-static int launch_tc(Run& r, const TcLayer& T, const float* bias, const float* x, float* y, const float* res, int t_len,
-                     int mul, float slope, float scale, int accumulate) {
+// one generator conv on the tensor cores (3xTF32), channels-last in/out.  t_len / mul are in INPUT steps.
+static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const float* res, int t_len, int mul, float slope,
+                     float scale, int accumulate, int family) {
   TcConvArgs a{};
-  a.x = x; a.x_bs = (long long)T.C * r.P * mul;
+  a.x = x; a.x_bs = (long long)T.Cin * r.P * mul;
   a.w = r.c->d_tcw + T.w_off;
-  a.bias = bias;
-  a.y = y; a.y_bs = a.x_bs;
+  a.bias = r.c->d_tcw + T.b_off;
+  a.y = y; a.y_bs = (long long)T.Ntot * r.P * mul;
   a.r = res;
   a.lens = r.glens; a.tmax = r.Tmax; a.mul = mul;
-  a.C = T.C; a.K = T.K; a.DIL = T.DIL;
+  a.Cin = T.Cin; a.Ntot = T.Ntot; a.K = T.K; a.DIL = T.DIL;
   a.slope = slope; a.scale = scale; a.accumulate = accumulate;
-  dim3 grid((t_len + TC_MT * 128 - 1) / (TC_MT * 128), T.C / T.TN, r.B);
+  const int steps = (T.TN == 128 ? TcCfg<128>::MT : TcCfg<64>::MT) * 128;
+  dim3 grid((t_len + steps - 1) / steps, T.Ntot / T.TN, r.B);
   TRY(prof_begin(r));
   if (T.TN == 128) tcconv_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, r.st>>>(a);
   else if (T.TN == 64) tcconv_kernel<64><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, r.st>>>(a);
@@ -661,7 +682,9 @@ static int launch_tc(Run& r, const TcLayer& T, const float* bias, const float* x
   CK(cudaGetLastError());
   r.c->launches++;
   const double units = (double)r.B * t_len;
-  TRY(prof_end(r, T.TN == 128 ? V_TC128 : T.TN == 64 ? V_TC64 : V_TC32, 1, 2.0 * T.C * T.C * T.K * units, 8.0 * T.C * units));
+  const int eff_k = family == 1 ? T.K : 2;   // polyphase transposed conv: 2 of the 3 packed taps are non-zero per row
+  TRY(prof_end(r, T.TN == 128 ? V_TC128 : T.TN == 64 ? V_TC64 : V_TC32, family, 2.0 * T.Cin * T.Ntot * eff_k * units,
+               4.0 * (T.Cin + T.Ntot) * units));
   return OVC_OK;
 }
 
@@ -828,6 +851,49 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
     TRY(tap(r, "dec.pre", ws + W.dpre, 512, Tmax, P));
   }
   float* bufA = ws + W.bufA; float* bufB = ws + W.bufB; float* bufC = ws + W.bufC; float* bufD = ws + W.bufD;
+  if (c->precision == 1) {
+    // ---- tensor-core generator: channels-last [t][C] from conv_pre's output to conv_post's input.
+    // ConvTranspose1d = polyphase conv Cin -> s*Cout whose row n IS output rows s*n .. s*n+s-1 of the
+    // channels-last result; ResBlock convs = tcconv with fused lrelu / bias / residual / MRF average.
+    float* bufE = ws + W.bufE;
+    float* bufF = ws + W.bufF;   // [C][T] scratch for debug taps
+    TRY(launch_transpose(r, ws + W.dpre, bufE, 512, P));
+    const float* stage_in = bufE;
+    int cin = 512, up = 1;
+    auto tap_cl = [&](const char* nm, const float* cl, int C, int T_, int pitch) -> int {
+      if (!c->debug) return OVC_OK;
+      TRY(launch_transpose(r, cl, bufF, pitch, C));
+      return tap(r, nm, bufF, C, T_, pitch);
+    };
+    for (int i = 0; i < 4; ++i) {
+      const int s = c->hp.upsample_rates[i];
+      const int cout = cin / 2, up_out = up * s;
+      const int Tlen = Tmax * up_out, pitch_out = P * up_out;
+      char nm[32];
+      TRY(launch_tc(r, c->tc_ups[i], stage_in, bufA, nullptr, Tmax * up, up, 0.1f, 1.f, 0, 0));
+      snprintf(nm, sizeof nm, "dec.ups%d", i);
+      TRY(tap_cl(nm, bufA, cout, Tlen, pitch_out));
+      for (int j = 0; j < 3; ++j)
+        for (int d = 0; d < 3; ++d) {
+          const float* xin = d == 0 ? bufA : bufB;
+          TRY(launch_tc(r, c->tc_c1[i * 3 + j][d], xin, bufC, nullptr, Tlen, up_out, 0.1f, 1.f, 0, 1));
+          float* yout = d < 2 ? bufB : bufD;
+          TRY(launch_tc(r, c->tc_c2[i * 3 + j][d], bufC, yout, xin, Tlen, up_out, 0.1f,
+                        (d == 2 && j == 2) ? 1.0f / 3.0f : 1.f, (d == 2 && j > 0) ? 1 : 0, 1));
+        }
+      snprintf(nm, sizeof nm, "dec.stage%d", i);
+      TRY(tap_cl(nm, bufD, cout, Tlen, pitch_out));
+      stage_in = bufD;   // the next upsampling consumes xs before that stage's MRF rewrites bufD (stream order)
+      cin = cout; up = up_out;
+    }
+    const int y_len = Tmax * up;
+    dim3 grid((y_len + 255) / 256, B);
+    conv_post_cl_kernel<32><<<grid, 256, 0, st>>>(stage_in, 32LL * P * up, c->d_w + c->post_w_off, o_hat, (long long)y_len,
+                                                 y_len, r.glens, Tmax, up);
+    CK(cudaGetLastError());
+    c->launches++;
+    return OVC_OK;
+  }
   const float* stage_in = ws + W.dpre;
   int cin = 512, up = 1;
   for (int i = 0; i < 4; ++i) {
@@ -850,24 +916,6 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
     // MRF: xs = sum_j ResBlock1_j(x) / 3 (models.py:280-286; ResBlock1 = modules.py:296-309)
     const long long bsC = (long long)cout * pitch_out;
     const int Tlen = Tmax * up_out;
-    float* stage_out = bufD;
-    if (c->precision == 1) {
-      // tensor-core path: channels-last [t][C] inside the MRF, transposed at its boundary
-      float* bufE = ws + W.bufE;
-      float* bufF = ws + W.bufF;
-      TRY(launch_transpose(r, bufA, bufE, cout, pitch_out));
-      for (int j = 0; j < 3; ++j)
-        for (int d = 0; d < 3; ++d) {
-          const float* xin = d == 0 ? bufE : bufB;
-          TRY(launch_tc(r, c->tc_c1[i * 3 + j][d], c->d_w + c->rb_c1[i * 3 + j][d].b_off, xin, bufC, nullptr, Tlen, up_out,
-                        0.1f, 1.f, 0));
-          float* yout = d < 2 ? bufB : bufD;
-          TRY(launch_tc(r, c->tc_c2[i * 3 + j][d], c->d_w + c->rb_c2[i * 3 + j][d].b_off, bufC, yout, xin, Tlen, up_out, 0.1f,
-                        (d == 2 && j == 2) ? 1.0f / 3.0f : 1.f, (d == 2 && j > 0) ? 1 : 0));
-        }
-      TRY(launch_transpose(r, bufD, bufF, pitch_out, cout));
-      stage_out = bufF;
-    } else {
     for (int j = 0; j < 3; ++j) {
       const int K = c->hp.resblock_kernel_sizes[j];
       for (int d = 0; d < 3; ++d) {
@@ -897,10 +945,9 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
         TRY(launch(r, c->rb_c2[i * 3 + j][d], b, Tlen, true, fl, by));
       }
     }
-    }
     char nm[32]; snprintf(nm, sizeof nm, "dec.stage%d", i);
-    TRY(tap(r, nm, stage_out, cout, Tlen, pitch_out));
-    stage_in = stage_out;
+    TRY(tap(r, nm, bufD, cout, Tlen, pitch_out));
+    stage_in = bufD;
     cin = cout; up = up_out;
   }
   // leaky_relu(0.01) + conv_post + tanh (models.py:287-289)

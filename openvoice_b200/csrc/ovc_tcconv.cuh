@@ -6,7 +6,7 @@
 // a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with tf32-exact high parts and fp32 remainders (error ~1e-6,
 // i.e. fp32-grade; tools/tc_gemm_test.cu), accumulated in fp32 in TMEM by tcgen05.mma.kind::tf32.
 //
-// One CTA = 512 time steps (4 MMA tiles of M=128) x TN output channels (TMEM: 4*TN columns).
+// One CTA = MT MMA tiles of 128 time steps x TN output channels (two fp32 accumulators each in TMEM).
 // K-major, no-swizzle operand tiles (see ovc_tc.cuh): a convolution tap is a 16-byte-per-row shift
 // of the A descriptor's start address, so all taps (any dilation) read ONE staged halo tile.
 // Warp roles (192 threads):
@@ -22,27 +22,34 @@
 namespace ovc {
 
 struct TcConvArgs {
-  const float* x; long long x_bs;     // [B][Lpitch][C]
-  const float* w;                      // packed [n_tiles][C/8][K][2 (hi|lo)][2 (k chunk)][TN][4]
-  const float* bias;                   // [C]
-  float* y; long long y_bs;            // [B][Lpitch][C]
+  const float* x; long long x_bs;     // [B][Lpitch][Cin]
+  const float* w;                      // packed [n_tiles][Cin/8][K][2 (hi|lo)][2 (k chunk)][TN][4]
+  const float* bias;                   // [Ntot]
+  float* y; long long y_bs;            // [B][Lpitch][Ntot]
   const float* r;                      // residual, same geometry as y (nullable)
   const long long* lens; int tmax; int mul;   // valid steps = min(tmax, lens[b]) * mul   (lens NULL -> tmax)
-  int C; int K; int DIL;
+  int Cin; int Ntot; int K; int DIL;   // Ntot = output row width (C for a ResBlock conv, stride*Cout for a polyphase transposed conv)
   float slope; float scale; int accumulate;
 };
 
-constexpr int TC_MT = 4;                 // MMA tiles (of 128 steps) per CTA
-constexpr int TC_ROWS = 576;             // staged rows per buffer (512 + 2*25 halo, padded)
+constexpr int TC_ROWS = 576;             // staged rows per buffer (<= 512 + 2*25 halo, padded)
 constexpr int TC_SLOTS = 8;              // weight ring depth
 constexpr int TC_THREADS = 192;
 
+// The tensor core ADDS into the TMEM accumulator with truncation: over ~10^3 accumulation steps a single
+// accumulator drifts by ~6e-5 of the output rms toward zero (tools/tc_acc_test.cu).  The two low-order passes
+// (a_lo*b_hi, a_hi*b_lo; 2^-11 of the result) therefore get their OWN accumulator, so the main one sees a third
+// of the steps and the small terms are summed at their own scale; the epilogue adds the two in fp32
+// (measured 2.0e-5 vs 6.1e-5; a plain fp32 fmaf chain has 1.0e-5).  TMEM columns = 2 * MT * TN <= 512.
 template <int TN>
 struct TcCfg {
+  // accumulation steps = 3 * Cin/8 * K: only the wide layers (C >= 128 -> TN = 128) are long enough to drift
+  static constexpr bool LOACC = TN == 128;
+  static constexpr int MT = TN == 128 ? 2 : 4;                   // MMA tiles (of 128 steps) per CTA
   static constexpr int A_BUF_FLOATS = 2 * 2 * TC_ROWS * 4;       // [hi|lo][k chunk][row][4]
   static constexpr int B_SLOT_FLOATS = 2 * 2 * TN * 4;           // [hi|lo][k chunk][n][4]
   static constexpr size_t SMEM_BYTES = 256 + sizeof(float) * (2 * A_BUF_FLOATS + TC_SLOTS * B_SLOT_FLOATS);
-  static constexpr uint32_t TMEM_COLS = TC_MT * TN;              // 128 / 256 / 512
+  static constexpr uint32_t TMEM_COLS = (LOACC ? 2 : 1) * MT * TN;   // 128 (TN 32) / 256 (TN 64) / 512 (TN 128)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -60,15 +67,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
   uint64_t* a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 12, *acc_full = bars + 20;
 
   const int b = blockIdx.z;
-  const int t0 = blockIdx.x * (TC_MT * 128);
+  constexpr int MT = Cfg::MT;
+  const int t0 = blockIdx.x * (MT * 128);
   const int n0 = blockIdx.y * TN;
   const int lim = (a.lens ? (int)min((long long)a.tmax, a.lens[b]) : a.tmax) * a.mul;
   if (t0 >= lim) return;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = (a.K - 1) / 2 * a.DIL;
-  const int rows = TC_MT * 128 + 2 * H;
-  const int nk8 = a.C / 8;
+  const int rows = MT * 128 + 2 * H;
+  const int nk8 = a.Cin / 8;
 
   if (tid == 0) {
     mbar_init(&a_full[0], 128); mbar_init(&a_full[1], 128);
@@ -119,15 +127,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
           const uint64_t bd_lo = tc::make_desc(b_base + B_LO_OFF, LBO_B, SBO);
           const bool first = (k8 == 0 && tap == 0);
 #pragma unroll
-          for (int mt = 0; mt < TC_MT; ++mt) {
+          for (int mt = 0; mt < MT; ++mt) {
             // output step (t0 + mt*128 + i) reads staged row (mt*128 + i + tap*DIL): the halo tile starts at t0 - H
             const uint32_t a_off = (uint32_t)(mt * 128 + tap * a.DIL) * 16;
             const uint64_t ad_hi = tc::make_desc(a_base + a_off, LBO_A, SBO);
             const uint64_t ad_lo = tc::make_desc(a_base + A_LO_OFF + a_off, LBO_A, SBO);
             const uint32_t d = tmem_d + mt * TN;
+            const uint32_t dl = Cfg::LOACC ? tmem_d + (MT + mt) * TN : d;   // low-order terms: own accumulator
             tc::mma_tf32(d, ad_hi, bd_hi, idesc, !first);
-            tc::mma_tf32(d, ad_lo, bd_hi, idesc, true);
-            tc::mma_tf32(d, ad_hi, bd_lo, idesc, true);
+            tc::mma_tf32(dl, ad_lo, bd_hi, idesc, Cfg::LOACC ? !first : true);
+            tc::mma_tf32(dl, ad_hi, bd_lo, idesc, true);
           }
           tc::mma_commit(&b_empty[slot]);       // slot reusable once these MMAs have read it
         }
@@ -145,17 +154,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
       mbar_wait(&a_empty[buf], ((k8 >> 1) & 1) ^ 1);
       float* ah = abuf + buf * Cfg::A_BUF_FLOATS;
       float* al = ah + 2 * TC_ROWS * 4;
-      for (int i = pt; i < items; i += 128) {
-        const int row = i >> 1, kc = i & 1;
-        const int t = t0 - H + row;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0 && t < lim) v = *reinterpret_cast<const float4*>(xb + (size_t)t * a.C + k8 * 8 + kc * 4);
-        v.x = lrelu(v.x, a.slope); v.y = lrelu(v.y, a.slope); v.z = lrelu(v.z, a.slope); v.w = lrelu(v.w, a.slope);
-        float4 hi, lo;
-        tc::split_tf32(v.x, hi.x, lo.x); tc::split_tf32(v.y, hi.y, lo.y);
-        tc::split_tf32(v.z, hi.z, lo.z); tc::split_tf32(v.w, hi.w, lo.w);
-        *reinterpret_cast<float4*>(ah + (kc * TC_ROWS + row) * 4) = hi;
-        *reinterpret_cast<float4*>(al + (kc * TC_ROWS + row) * 4) = lo;
+      // all global loads of a batch are issued before any is consumed (the loop is latency-, not bandwidth-bound)
+      constexpr int PB = 5;
+      for (int i0 = pt; i0 < items; i0 += 128 * PB) {
+        float4 v[PB];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+          const int i = i0 + 128 * u;
+          const int row = i >> 1, kc = i & 1;
+          const int t = t0 - H + row;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < items && t >= 0 && t < lim) v[u] = *reinterpret_cast<const float4*>(xb + (size_t)t * a.Cin + k8 * 8 + kc * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+          const int i = i0 + 128 * u;
+          if (i >= items) break;
+          const int row = i >> 1, kc = i & 1;
+          float4 q = v[u];
+          q.x = lrelu(q.x, a.slope); q.y = lrelu(q.y, a.slope); q.z = lrelu(q.z, a.slope); q.w = lrelu(q.w, a.slope);
+          float4 hi, lo;
+          tc::split_tf32(q.x, hi.x, lo.x); tc::split_tf32(q.y, hi.y, lo.y);
+          tc::split_tf32(q.z, hi.z, lo.z); tc::split_tf32(q.w, hi.w, lo.w);
+          *reinterpret_cast<float4*>(ah + (kc * TC_ROWS + row) * 4) = hi;
+          *reinterpret_cast<float4*>(al + (kc * TC_ROWS + row) * 4) = lo;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async) proxy
       mbar_arrive(&a_full[buf]);
@@ -167,36 +190,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
     float* yb = a.y + (size_t)b * a.y_bs;
     const float* rb = a.r ? a.r + (size_t)b * a.y_bs : nullptr;
 #pragma unroll 1
-    for (int mt = 0; mt < TC_MT; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       const int t = t0 + mt * 128 + lane_base + lane;
       const bool ok = t < lim;
-      float* yp = yb + (size_t)t * a.C + n0;
-      const float* rp = rb ? rb + (size_t)t * a.C + n0 : nullptr;
+      float* yp = yb + (size_t)t * a.Ntot + n0;
+      const float* rp = rb ? rb + (size_t)t * a.Ntot + n0 : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 8) {
-        float v[8];
-        tc::tmem_ld8(tmem_d + ((uint32_t)lane_base << 16) + mt * TN + c0, v);
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)lane_base << 16) + mt * TN + c0, v);
+        if constexpr (Cfg::LOACC) {
+          float lo[32];
+          tc::tmem_ld32(tmem_d + ((uint32_t)lane_base << 16) + (MT + mt) * TN + c0, lo);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += lo[i];
+        }
         if (ok) {
-          const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n0 + c0);
-          const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + 4 * q);
+            v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+          }
           if (rp) {
-            const float4 r0 = *reinterpret_cast<const float4*>(rp + c0), r1 = *reinterpret_cast<const float4*>(rp + c0 + 4);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 rq = *reinterpret_cast<const float4*>(rp + c0 + 4 * q);
+              v[4 * q] += rq.x; v[4 * q + 1] += rq.y; v[4 * q + 2] += rq.z; v[4 * q + 3] += rq.w;
+            }
           }
           if (a.accumulate) {
-            const float4 y0 = *reinterpret_cast<const float4*>(yp + c0), y1 = *reinterpret_cast<const float4*>(yp + c0 + 4);
-            v[0] = y0.x + v[0]; v[1] = y0.y + v[1]; v[2] = y0.z + v[2]; v[3] = y0.w + v[3];
-            v[4] = y1.x + v[4]; v[5] = y1.y + v[5]; v[6] = y1.z + v[6]; v[7] = y1.w + v[7];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 yq = *reinterpret_cast<const float4*>(yp + c0 + 4 * q);
+              v[4 * q] = yq.x + v[4 * q]; v[4 * q + 1] = yq.y + v[4 * q + 1];
+              v[4 * q + 2] = yq.z + v[4 * q + 2]; v[4 * q + 3] = yq.w + v[4 * q + 3];
+            }
           }
           if (a.scale != 1.f) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= a.scale;
+            for (int i = 0; i < 32; ++i) v[i] *= a.scale;
           }
-          *reinterpret_cast<float4*>(yp + c0) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(yp + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(yp + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
       }
     }
@@ -204,6 +240,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
   tc::fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+}
+
+// conv_post on channels-last input: y[b, t] = tanh(sum_{k<7, ci<C} w[ci, k] * lrelu_0.01(x[b, t+k-3, ci]))
+// (models.py:287-289).  One thread per output sample; the 7 input rows (128 B each) are shared through L1.
+template <int C>
+__global__ void __launch_bounds__(256) conv_post_cl_kernel(const float* __restrict__ x, long long x_bs,
+                                                           const float* __restrict__ w, float* __restrict__ y,
+                                                           long long y_bs, int y_len, const long long* lens, int tmax,
+                                                           int mul) {
+  __shared__ float ws[7][C];   // transposed: [k][ci]
+  for (int i = threadIdx.x; i < C * 7; i += blockDim.x) ws[i % 7][i / 7] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int lim = (lens ? (int)min((long long)tmax, lens[b]) : tmax) * mul;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= y_len) return;
+  float acc = 0.f;
+  if (t < lim) {
+    const float* xb = x + (size_t)b * x_bs;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int tt = t + k - 3;
+      if (tt < 0 || tt >= lim) continue;
+      const float4* row = reinterpret_cast<const float4*>(xb + (size_t)tt * C);
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q) {
+        const float4 v = row[q];
+        acc = fmaf(ws[k][4 * q + 0], v.x > 0.f ? v.x : 0.01f * v.x, acc);
+        acc = fmaf(ws[k][4 * q + 1], v.y > 0.f ? v.y : 0.01f * v.y, acc);
+        acc = fmaf(ws[k][4 * q + 2], v.z > 0.f ? v.z : 0.01f * v.z, acc);
+        acc = fmaf(ws[k][4 * q + 3], v.w > 0.f ? v.w : 0.01f * v.w, acc);
+      }
+    }
+    acc = tanhf(acc);
+  }
+  y[(size_t)b * y_bs + t] = acc;
 }
 
 // [B][C][pitch] <-> [B][pitch][C] tiled transpose (32x32 through shared memory)

@@ -28,6 +28,12 @@ def hps():
 _native_cache = {}
 
 
+def pytest_generate_tests(metafunc):
+    # every GPU parity test that takes `native` runs in both arithmetic modes of the generator
+    if "native" in metafunc.fixturenames:
+        metafunc.parametrize("native", ["fp32", "tf32x3"], indirect=True)
+
+
 def get_native(zero_g=False):
     """One NativeSynthesizer per flavour for the whole session (weights: 128 MB)."""
     import copy
@@ -44,9 +50,12 @@ def get_native(zero_g=False):
     return _native_cache[zero_g]
 
 
-@pytest.fixture(scope="session")
-def native():
-    return get_native(False)
+@pytest.fixture
+def native(request):
+    m = get_native(False)
+    m.native.set_precision(getattr(request, "param", "fp32"))
+    yield m
+    m.native.set_precision("fp32")
 
 
 @pytest.fixture(scope="session")
