@@ -199,8 +199,10 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU reference arm")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips in the cpu_baseline sample of the native arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("OVC_PRECISION", "fp32"), choices=["fp32", "tf32x3"],
-                    help="generator ResBlock conv arithmetic: fp32 FFMA2 (default) or 3xTF32 tensor cores")
+    ap.add_argument("--precision", default=os.environ.get("OVC_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32"],
+                    help="generator conv arithmetic: tf32x3 = split-precision tensor cores (default, fp32-grade), "
+                         "fp32 = CUDA-core FFMA2, tf32 = single-pass TF32 (the reference's own GPU default)")
+    ap.add_argument("--no-modes", action="store_true", help="skip the short side measurements of the other precisions")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,10 +239,9 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         cfg = os.path.join(td, "config.json")
         json.dump(O.DEFAULT_HPARAMS, open(cfg, "w"))
-        conv = ToneColorConverter(cfg, device=dev, enable_watermark=False)
+        conv = ToneColorConverter(cfg, device=dev, enable_watermark=False, precision=args.precision)
     conv.model.load_state_dict(sd)
     del sd
-    conv.model.native.set_precision(args.precision)
 
     B, secs = args.batch, args.secs
     waves = [synth_wave(rank * B + i, secs) for i in range(B)]
@@ -287,6 +288,23 @@ def main():
     prof = native.profile_read()
     native.profile_enable(False)
     launches_per_call = native.last_launch_count
+
+    # ---- the other arithmetic modes, short (2 timed steps), device-resident only
+    modes = {}
+    if not args.no_modes:
+        for mode in ("fp32", "tf32x3", "tf32"):
+            if mode == args.precision:
+                continue
+            native.set_precision(mode)
+            device_step(1)
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            device_step(2); device_step(3)
+            m1.record()
+            barrier()
+            modes[mode] = world * audio_s_step / (max_over_ranks(m0.elapsed_time(m1)) / 2 * 1e-3)
+        native.set_precision(args.precision)
 
     # ---- end-to-end leg: host numpy in, host numpy out, through the public API
     def e2e_step():
@@ -335,21 +353,38 @@ def main():
                         "algorithmic in+out+residual = 677 MB")
     except Exception:
         pass
-    roofline = {
-        "kernel": "conv1d_f32<EPI_LINEAR> (generator ResBlock1 convs, 72 launches per call)",
-        "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-        "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-        "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_dev,
-        "binding": "fp32 FFMA (dense contraction, SURVEY.md section 8d)",
-        "ffma": {"achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FFMA_PEAK_TFLOPS,
-                 "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"},
-    }
+    if args.precision == "fp32":
+        roofline = {
+            "kernel": "conv1d_f32<EPI_LINEAR> (generator ResBlock1 convs, 72 launches per call)",
+            "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+            "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+            "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_dev,
+            "binding": "fp32 FFMA (dense contraction, SURVEY.md section 8d)",
+            "ffma": {"achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FFMA_PEAK_TFLOPS,
+                     "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"},
+        }
+    else:
+        # tensor-core modes: the MMA rate is what binds.  TF32 runs at half the bf16 rate; every algorithmic FLOP
+        # costs 3 tensor FLOPs in the split-precision mode.
+        passes = 3 if args.precision == "tf32x3" else 1
+        tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        roofline = {
+            "kernel": "tcconv_kernel<TN> (generator ResBlock1 convs on tcgen05, 72 launches per call)",
+            "bound": "tensor", "achieved": ach_tf * passes, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": ach_tf * passes / tf32_peak, "traffic": None,
+            "peak_source": ("measured" if "bf16_tflops_sustained" in peaks else "fallback") + " bf16 sustained / 2 (TF32 rate)",
+            "algorithmic_tflops": ach_tf, "mma_passes": passes,
+            "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_dev,
+            "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src},
+        }
     value = world * audio_s_step / (ms_dev * 1e-3)
     e2e_val = world * audio_s_step / (ms_e2e * 1e-3)
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split-precision tensor-core generator convs, fp32 FFMA2 elsewhere)",
+                  "tf32": "tf32 (single-pass tensor-core generator convs, fp32 elsewhere)"}[args.precision],
+        "data": "synthetic", "precision": args.precision, "modes_audio_s_per_s": modes,
         "config": {"workload": f"ToneColorConverter.convert_batch, batch {B} x {secs:g} s clips @ {SR} Hz per GPU "
                                "(BASELINE configs[1]), seeded synthetic checkpoint, tau 0.3, in-kernel Philox noise",
                    "batch_per_gpu": B, "global_batch": B * world, "secs": secs, "frames": T,

@@ -136,7 +136,9 @@ OVC_API int ovc_convert_waveform(ovc_ctx* ctx, const float* wav, const int64_t* 
  *   0 (default)  fp32 FFMA2 on the CUDA cores
  *   1            split-precision 3xTF32 on the 5th-gen tensor cores (tcgen05 + TMEM): every product is
  *                a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with tf32-exact high parts, fp32 accumulation --
- *                fp32-grade (~1e-6) error, same parity gate as mode 0                               */
+ *                fp32-grade error (3e-5 of the output rms measured), same parity gate as mode 0
+ *   2            single-pass TF32 on the tensor cores: the precision the REFERENCE itself gets on a GPU by
+ *                default (torch.backends.cudnn.allow_tf32 = True); ~4e-3 of the output rms, own looser gate */
 OVC_API int ovc_set_precision(ovc_ctx* ctx, int mode);
 
 /* Number of kernels the last ovc_voice_conversion / ovc_convert_waveform call launched. */

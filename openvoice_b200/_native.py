@@ -175,7 +175,7 @@ class NativeConverter:
 
     def set_precision(self, mode: str):
         """'fp32' (CUDA-core FFMA2, default) or 'tf32x3' (split-precision tensor-core ResBlock convs)."""
-        m = {"fp32": 0, "tf32x3": 1}[mode]
+        m = {"fp32": 0, "tf32x3": 1, "tf32": 2}[mode]
         _check(self.lib, self.lib.ovc_set_precision(self.handle, m), "ovc_set_precision")
         self.precision = mode
 

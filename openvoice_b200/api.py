@@ -74,7 +74,11 @@ class NativeSynthesizer:
     ``n_speakers == 0`` converter (openvoice/models.py:399-465): ``voice_conversion``,
     ``ref_enc``, ``load_state_dict``, ``eval``, ``zero_g``."""
 
-    def __init__(self, hps, device: str):
+    def __init__(self, hps, device: str, precision: Optional[str] = None):
+        """``precision``: arithmetic of the generator's ResBlock / upsampling convolutions --
+        ``"tf32x3"`` (default; split-precision tcgen05 tensor cores, fp32-grade: 3e-5 of the output rms),
+        ``"fp32"`` (CUDA-core FFMA2 everywhere, 8e-6) or ``"tf32"`` (single-pass TF32, what the reference
+        itself gets on a GPU through cuDNN's allow_tf32 default; ~1e-2).  Env override: OVC_PRECISION."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("openvoice_b200 runs on CUDA (sm_100a) only; there is no CPU path")
@@ -87,6 +91,8 @@ class NativeSynthesizer:
                              "base-speaker TTS front half is out of this build's scope")
         index = dev.index if dev.index is not None else torch.cuda.current_device()
         self.native = NativeConverter(hps, index)
+        self.precision = precision or os.environ.get("OVC_PRECISION", "tf32x3")
+        self.native.set_precision(self.precision)
         self.spec_channels = hps.data.filter_length // 2 + 1
         self.ref_enc = ReferenceEncoder(self.spec_channels, int(getattr(hps.model, "gin_channels", 256)))
         self._expected = hot_path_keys(hps) + ref_enc_keys()
@@ -149,11 +155,11 @@ class NativeSynthesizer:
 class OpenVoiceBaseClass(object):
     """openvoice/api.py:14-39."""
 
-    def __init__(self, config_path, device="cuda:0"):
+    def __init__(self, config_path, device="cuda:0", precision=None):
         if "cuda" in device:
             assert torch.cuda.is_available()
         hps = utils.get_hparams_from_file(config_path)
-        self.model = NativeSynthesizer(hps, device).eval()
+        self.model = NativeSynthesizer(hps, device, precision=precision).eval()
         self.hps = hps
         self.device = device
 

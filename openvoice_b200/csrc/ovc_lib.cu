@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -507,9 +508,9 @@ static int finalize(ovc_ctx* c) {
   CK(cudaMemcpy(c->d_tcw, c->h_tcw.data(), c->h_tcw.size() * sizeof(float), cudaMemcpyHostToDevice));
   c->h_tcw.clear();
   c->h_tcw.shrink_to_fit();
-  CK(cudaFuncSetAttribute(tcconv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<128>::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tcconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<64>::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tcconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<32>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_kernel<128, TC_CL128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<128>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<64>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<32>::SMEM_BYTES));
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
   CK(cudaMalloc(&c->d_cond_wrow, wrow.size() * sizeof(int)));
@@ -673,12 +674,25 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   a.lens = r.glens; a.tmax = r.Tmax; a.mul = mul;
   a.Cin = T.Cin; a.Ntot = T.Ntot; a.K = T.K; a.DIL = T.DIL;
   a.slope = slope; a.scale = scale; a.accumulate = accumulate;
+  a.passes = r.c->precision == 2 ? 1 : 3;
+  {
+    const char* e = getenv("OVC_TC_DBG");   // timing ablations only (tools/layer_report.py --ablate)
+    a.dbg = e ? atoi(e) : 0;
+  }
   const int steps = (T.TN == 128 ? TcCfg<128>::MT : TcCfg<64>::MT) * 128;
   dim3 grid((t_len + steps - 1) / steps, T.Ntot / T.TN, r.B);
   TRY(prof_begin(r));
-  if (T.TN == 128) tcconv_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, r.st>>>(a);
-  else if (T.TN == 64) tcconv_kernel<64><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, r.st>>>(a);
-  else tcconv_kernel<32><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, r.st>>>(a);
+  if (T.TN == 128) {
+    grid.x = (grid.x + TC_CL128 - 1) / TC_CL128 * TC_CL128;   // whole clusters along time
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<128>::SMEM_BYTES; cfg.stream = r.st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TC_CL128; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, tcconv_kernel<128, TC_CL128>, a));
+  } else if (T.TN == 64) tcconv_kernel<64, 1><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, r.st>>>(a);
+  else tcconv_kernel<32, 1><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, r.st>>>(a);
   CK(cudaGetLastError());
   r.c->launches++;
   const double units = (double)r.B * t_len;
@@ -851,7 +865,7 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
     TRY(tap(r, "dec.pre", ws + W.dpre, 512, Tmax, P));
   }
   float* bufA = ws + W.bufA; float* bufB = ws + W.bufB; float* bufC = ws + W.bufC; float* bufD = ws + W.bufD;
-  if (c->precision == 1) {
+  if (c->precision >= 1) {
     // ---- tensor-core generator: channels-last [t][C] from conv_pre's output to conv_post's input.
     // ConvTranspose1d = polyphase conv Cin -> s*Cout whose row n IS output rows s*n .. s*n+s-1 of the
     // channels-last result; ResBlock convs = tcconv with fused lrelu / bias / residual / MRF average.
@@ -1099,7 +1113,7 @@ int ovc_convert_waveform(ovc_ctx* c, const float* wav, const int64_t* wav_length
 
 int ovc_set_precision(ovc_ctx* c, int mode) {
   if (!c) return fail(OVC_ERR_INVALID, "null context");
-  if (mode != 0 && mode != 1) return fail(OVC_ERR_INVALID, "precision mode must be 0 (fp32 FFMA) or 1 (3xTF32 tensor cores)");
+  if (mode < 0 || mode > 2) return fail(OVC_ERR_INVALID, "precision mode must be 0 (fp32 FFMA2), 1 (3xTF32 tensor cores) or 2 (single-pass TF32)");
   c->precision = mode;
   return OVC_OK;
 }

@@ -9,9 +9,10 @@
 // One CTA = MT MMA tiles of 128 time steps x TN output channels (two fp32 accumulators each in TMEM).
 // K-major, no-swizzle operand tiles (see ovc_tc.cuh): a convolution tap is a 16-byte-per-row shift
 // of the A descriptor's start address, so all taps (any dilation) read ONE staged halo tile.
-// Warp roles (192 threads):
+// Warp roles (224 threads):
 //   warp 0      : TMA bulk copies of pre-split, pre-laid-out weight slots [tap][hi|lo] into an 8-slot ring
-//   warp 1      : single-thread tcgen05.mma issue; tcgen05.commit releases ring slots / A buffers
+//   warps 1, 6  : one tcgen05.mma-issuing thread each (half of the MMA tiles); tcgen05.commit releases ring
+//                 slots / A buffers
 //   warps 2..5  : A producers -- global (16 B, zero-filled past the utterance) -> lrelu -> hi/lo split
 //                 -> shared (2 buffers, 8 input channels each); afterwards the epilogue warps:
 //                 tcgen05.ld -> bias / residual / MRF accumulate / scale -> global
@@ -30,11 +31,16 @@ struct TcConvArgs {
   const long long* lens; int tmax; int mul;   // valid steps = min(tmax, lens[b]) * mul   (lens NULL -> tmax)
   int Cin; int Ntot; int K; int DIL;   // Ntot = output row width (C for a ResBlock conv, stride*Cout for a polyphase transposed conv)
   float slope; float scale; int accumulate;
+  int dbg;      // ablation switches (timing experiments only): 1 skip A production, 2 skip epilogue, 4 skip MMAs
+  int passes;   // 3: split precision (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo); 1: single-pass TF32 (what cuDNN does by default)
 };
 
-constexpr int TC_ROWS = 576;             // staged rows per buffer (<= 512 + 2*25 halo, padded)
-constexpr int TC_SLOTS = 8;              // weight ring depth
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;           // warps: 0 TMA, 1 + 6 MMA issuers, 2..5 A producers / epilogue
+constexpr int TC_NISS = 2;                // MMA-issuing threads (each owns half of the CTA's MMA tiles)
+#ifndef OVC_TC_CL
+#define OVC_TC_CL 1
+#endif
+constexpr int TC_CL128 = OVC_TC_CL;      // CTAs per cluster of the wide variant (weight multicast across the cluster)
 
 // The tensor core ADDS into the TMEM accumulator with truncation: over ~10^3 accumulation steps a single
 // accumulator drifts by ~6e-5 of the output rms toward zero (tools/tc_acc_test.cu).  The two low-order passes
@@ -46,32 +52,73 @@ struct TcCfg {
   // accumulation steps = 3 * Cin/8 * K: only the wide layers (C >= 128 -> TN = 128) are long enough to drift
   static constexpr bool LOACC = TN == 128;
   static constexpr int MT = TN == 128 ? 2 : 4;                   // MMA tiles (of 128 steps) per CTA
-  static constexpr int A_BUF_FLOATS = 2 * 2 * TC_ROWS * 4;       // [hi|lo][k chunk][row][4]
+  static constexpr int ROWS = MT * 128 + 64;                     // staged rows per A buffer (tile + 2*25 halo, padded)
+  // the producers are latency-bound (ncu: long_scoreboard ~70 %): the 1-CTA/SM wide variant gets a deep pipeline,
+  // the narrow ones run 2 CTAs per SM and hide latency that way
+  static constexpr int NABUF = 2;                                // A stages (8 input channels each)
+  // weight streaming is latency-bound: throughput = ring bytes / L2 latency, so the wide variant (1 CTA per SM)
+  // spends all the shared memory it can on the ring (ablation: A production is hidden, the ring is not)
+  static constexpr int SLOTS = TN == 128 ? 20 : 8;               // weight ring depth
+  static constexpr int A_BUF_FLOATS = 2 * 2 * ROWS * 4;          // [hi|lo][k chunk][row][4]
   static constexpr int B_SLOT_FLOATS = 2 * 2 * TN * 4;           // [hi|lo][k chunk][n][4]
-  static constexpr size_t SMEM_BYTES = 256 + sizeof(float) * (2 * A_BUF_FLOATS + TC_SLOTS * B_SLOT_FLOATS);
+  // raw fp32 landing stages for the producers' cp.async prefetch (rows x 8 channels), RAWD chunks ahead
+  static constexpr int RAWD = TN == 128 ? 1 : 0;
+  static constexpr int RAW_FLOATS = ROWS * 8;
+  static constexpr size_t SMEM_BYTES =
+      512 + sizeof(float) * (NABUF * A_BUF_FLOATS + SLOTS * B_SLOT_FLOATS + (RAWD ? (RAWD + 1) * RAW_FLOATS : 0));
   static constexpr uint32_t TMEM_COLS = (LOACC ? 2 : 1) * MT * TN;   // 128 (TN 32) / 256 (TN 64) / 512 (TN 128)
 };
+
+// cluster helpers (2-CTA clusters share every weight slot: each CTA fetches half and multicasts it to both)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int TN>
-__global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs a) {
+template <int TN, int CL>
+__global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(const TcConvArgs a) {
   using Cfg = TcCfg<TN>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);   // [0..1] a_full, [2..3] a_empty, [4..11] b_full, [12..19] b_empty, [20] acc_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 21 * 8);
-  float* abuf = reinterpret_cast<float*>(smem_raw + 256);
-  float* bring = abuf + 2 * Cfg::A_BUF_FLOATS;
-  uint64_t* a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 12, *acc_full = bars + 20;
+  constexpr int NABUF = Cfg::NABUF, SLOTS = Cfg::SLOTS, ROWS = Cfg::ROWS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* a_full = bars, *a_empty = bars + NABUF, *b_full = bars + 2 * NABUF, *b_empty = b_full + SLOTS,
+            *acc_full = b_empty + SLOTS;
+  static_assert((2 * NABUF + 2 * SLOTS + 1) * 8 + 8 <= 512, "barrier area");
+  static_assert((NABUF & (NABUF - 1)) == 0, "NABUF must be a power of two");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* abuf = reinterpret_cast<float*>(smem_raw + 512);
+  float* bring = abuf + NABUF * Cfg::A_BUF_FLOATS;
 
   const int b = blockIdx.z;
   constexpr int MT = Cfg::MT;
   const int t0 = blockIdx.x * (MT * 128);
   const int n0 = blockIdx.y * TN;
   const int lim = (a.lens ? (int)min((long long)a.tmax, a.lens[b]) : a.tmax) * a.mul;
-  if (t0 >= lim) return;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  if (t0 - (int)crank * (MT * 128) >= lim) return;   // the whole cluster lies past the utterance (cluster-uniform)
+  const bool active = t0 < lim;                       // a padding CTA still takes part in the weight multicast
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = (a.K - 1) / 2 * a.DIL;
@@ -79,15 +126,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
   const int nk8 = a.Cin / 8;
 
   if (tid == 0) {
-    mbar_init(&a_full[0], 128); mbar_init(&a_full[1], 128);
-    mbar_init(&a_empty[0], 1); mbar_init(&a_empty[1], 1);
-    for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], TC_NISS); }
+    for (int i = 0; i < SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL * TC_NISS); }
+    mbar_init(acc_full, TC_NISS);
     fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc::fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // every CTA's barriers exist before any remote arrive / multicast
   tc::fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
@@ -95,65 +142,127 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
     // ------------------------------------------------------------ weight producer (TMA bulk)
     if (lane == 0) {
       const float* wt = a.w + (size_t)blockIdx.y * nk8 * a.K * Cfg::B_SLOT_FLOATS;
-      constexpr uint32_t BYTES = Cfg::B_SLOT_FLOATS * sizeof(float);
-      int it = 0;
-      for (int k8 = 0; k8 < nk8; ++k8)
-        for (int tap = 0; tap < a.K; ++tap, ++it) {
-          const int slot = it % TC_SLOTS, round = it / TC_SLOTS;
-          mbar_wait(&b_empty[slot], (round & 1) ^ 1);
-          mbar_expect_tx(&b_full[slot], BYTES);
-          tma_bulk_g2s(bring + slot * Cfg::B_SLOT_FLOATS, wt + (size_t)it * Cfg::B_SLOT_FLOATS, BYTES, &b_full[slot]);
-        }
+      // a slot is [hi | lo]; single-pass TF32 needs (and fetches) only the first half
+      const uint32_t BYTES = (a.passes == 3 ? Cfg::B_SLOT_FLOATS : Cfg::B_SLOT_FLOATS / 2) * sizeof(float);
+      const int PART = (int)(BYTES / sizeof(float)) / CL;
+      const int n_slots = nk8 * a.K;
+      int slot = 0;
+      uint32_t phase = 1;   // the first pass over the ring finds every slot free
+      for (int it = 0; it < n_slots; ++it) {
+        mbar_wait(&b_empty[slot], phase);
+        mbar_expect_tx(&b_full[slot], BYTES);
+        float* dst = bring + slot * Cfg::B_SLOT_FLOATS;
+        if (CL == 1) tma_bulk_g2s(dst, wt, BYTES, &b_full[slot]);
+        else tma_bulk_g2s_mcast(dst + crank * PART, wt + crank * PART, BYTES / CL, &b_full[slot], CMASK);
+        wt += Cfg::B_SLOT_FLOATS;
+        if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+      }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
+  } else if (warp == 1 || warp == 6) {
+    // ------------------------------------------------------------ MMA issuers (one thread each)
+    // The loop body is kept minimal on purpose: this single thread's instruction latency, not the tensor
+    // pipe, bounded the first version (112 SASS instructions per tap incl. two integer divisions).
+    // Descriptors differ only in their 14-bit start-address field, so they are advanced by plain adds.
     if (lane == 0) {
+      const int mt_lo = (warp == 1 ? 0 : MT / TC_NISS), mt_hi = mt_lo + MT / TC_NISS;
       const uint32_t idesc = tc::make_idesc_tf32(128, TN);
-      constexpr uint32_t LBO_A = TC_ROWS * 16, LBO_B = TN * 16, SBO = 128;
-      constexpr uint32_t A_LO_OFF = 2 * TC_ROWS * 16;        // bytes from hi to lo inside an A buffer
-      constexpr uint32_t B_LO_OFF = 2 * TN * 16;
-      int it = 0;
+      constexpr uint32_t LBO_A = ROWS * 16, LBO_B = TN * 16, SBO = 128;
+      constexpr uint32_t A_LO16 = (2 * ROWS * 16) >> 4;          // hi -> lo inside an A buffer, in 16-byte units
+      constexpr uint32_t B_LO16 = (2 * TN * 16) >> 4;
+      constexpr uint32_t SLOT16 = (Cfg::B_SLOT_FLOATS * 4) >> 4;
+      const uint64_t a_proto = tc::make_desc(0, LBO_A, SBO), b_proto = tc::make_desc(0, LBO_B, SBO);
+      const uint64_t b_ring = b_proto + (tc::smem_addr(bring) >> 4);
+      const uint32_t dil = (uint32_t)a.DIL;
+      const bool three = a.passes == 3;
+      int slot = 0;
+      uint32_t bphase = 0;
+      bool first = true;
       for (int k8 = 0; k8 < nk8; ++k8) {
-        const int buf = k8 & 1;
-        mbar_wait(&a_full[buf], (k8 >> 1) & 1);
+        const int buf = k8 & (NABUF - 1);
+        if (active) mbar_wait(&a_full[buf], (k8 / NABUF) & 1);
         tc::fence_after();
-        const uint32_t a_base = tc::smem_addr(abuf + buf * Cfg::A_BUF_FLOATS);
-        for (int tap = 0; tap < a.K; ++tap, ++it) {
-          const int slot = it % TC_SLOTS, round = it / TC_SLOTS;
-          mbar_wait(&b_full[slot], round & 1);
+        uint64_t a_cur = a_proto + (tc::smem_addr(abuf + buf * Cfg::A_BUF_FLOATS) >> 4);
+        for (int tap = 0; tap < a.K; ++tap) {
+          mbar_wait(&b_full[slot], bphase);
           tc::fence_after();
-          const uint32_t b_base = tc::smem_addr(bring + slot * Cfg::B_SLOT_FLOATS);
-          const uint64_t bd_hi = tc::make_desc(b_base, LBO_B, SBO);
-          const uint64_t bd_lo = tc::make_desc(b_base + B_LO_OFF, LBO_B, SBO);
-          const bool first = (k8 == 0 && tap == 0);
+          const uint64_t bd_hi = b_ring + (uint32_t)slot * SLOT16, bd_lo = bd_hi + B_LO16;
+          if (active && !(a.dbg & 4)) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            // output step (t0 + mt*128 + i) reads staged row (mt*128 + i + tap*DIL): the halo tile starts at t0 - H
-            const uint32_t a_off = (uint32_t)(mt * 128 + tap * a.DIL) * 16;
-            const uint64_t ad_hi = tc::make_desc(a_base + a_off, LBO_A, SBO);
-            const uint64_t ad_lo = tc::make_desc(a_base + A_LO_OFF + a_off, LBO_A, SBO);
-            const uint32_t d = tmem_d + mt * TN;
-            const uint32_t dl = Cfg::LOACC ? tmem_d + (MT + mt) * TN : d;   // low-order terms: own accumulator
-            tc::mma_tf32(d, ad_hi, bd_hi, idesc, !first);
-            tc::mma_tf32(dl, ad_lo, bd_hi, idesc, Cfg::LOACC ? !first : true);
-            tc::mma_tf32(dl, ad_hi, bd_lo, idesc, true);
+            for (int mt = mt_lo; mt < mt_hi; ++mt) {
+              // output step (t0 + mt*128 + i) reads staged row (mt*128 + i + tap*DIL): the halo tile starts at t0 - H
+              const uint64_t ad_hi = a_cur + mt * 128, ad_lo = ad_hi + A_LO16;
+              const uint32_t d = tmem_d + mt * TN;
+              const uint32_t dl = Cfg::LOACC ? tmem_d + (MT + mt) * TN : d;   // low-order terms: own accumulator
+              tc::mma_tf32(d, ad_hi, bd_hi, idesc, !first);
+              if (three) {
+                tc::mma_tf32(dl, ad_lo, bd_hi, idesc, Cfg::LOACC ? !first : true);
+                tc::mma_tf32(dl, ad_hi, bd_lo, idesc, true);
+              }
+            }
           }
-          tc::mma_commit(&b_empty[slot]);       // slot reusable once these MMAs have read it
+          first = false;
+          if (CL == 1) tc::mma_commit(&b_empty[slot]);       // slot reusable once these MMAs have read it
+          else mma_commit_mcast(&b_empty[slot], CMASK);      // ... in every CTA of the cluster
+          a_cur += dil;
+          if (++slot == SLOTS) { slot = 0; bphase ^= 1; }
         }
         tc::mma_commit(&a_empty[buf]);
       }
       tc::mma_commit(acc_full);
     }
-  } else {
+  } else if (active && warp >= 2 && warp <= 5) {
     // ------------------------------------------------------------ A producers, then epilogue
     const int pt = tid - 64;                                   // 0..127
     const float* xb = a.x + (size_t)b * a.x_bs;
     const int items = rows * 2;                                // (row, 16-byte half of the 8 channels)
+    if constexpr (Cfg::RAWD > 0) {
+      // deep prefetch: raw fp32 rows land by cp.async (zero-filled outside [0, lim)) RAWD chunks ahead; the
+      // conversion (lrelu, hi/lo split, operand layout) then runs shared -> shared on data this thread staged
+      constexpr int NST = Cfg::RAWD + 1;
+      float* raw = bring + SLOTS * Cfg::B_SLOT_FLOATS;
+      auto stage = [&](int k8) {
+        float* dst = raw + (k8 % NST) * Cfg::RAW_FLOATS;
+        for (int i = pt; i < ((a.dbg & 1) ? 0 : items); i += 128) {
+          const int row = i >> 1, kc = i & 1;
+          const int t = t0 - H + row;
+          const bool ok = (t >= 0 && t < lim);
+          const float* src = ok ? xb + (size_t)t * a.Cin + k8 * 8 + kc * 4 : xb;
+          cp_async16_zfill(dst + i * 4, src, ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      for (int k8 = 0; k8 < Cfg::RAWD; ++k8) {
+        if (k8 < nk8) stage(k8);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      for (int k8 = 0; k8 < nk8; ++k8) {
+        if (k8 + Cfg::RAWD < nk8) stage(k8 + Cfg::RAWD);
+        else asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count uniform
+        asm volatile("cp.async.wait_group %0;" ::"n"(Cfg::RAWD) : "memory");
+        const int buf = k8 % NABUF;
+        mbar_wait(&a_empty[buf], ((k8 / NABUF) & 1) ^ 1);
+        float* ah = abuf + buf * Cfg::A_BUF_FLOATS;
+        float* al = ah + 2 * ROWS * 4;
+        const float* src = raw + (k8 % NST) * Cfg::RAW_FLOATS;
+        for (int i = pt; i < ((a.dbg & 1) ? 0 : items); i += 128) {
+          const int row = i >> 1, kc = i & 1;
+          float4 q = *reinterpret_cast<const float4*>(src + i * 4);
+          q.x = lrelu(q.x, a.slope); q.y = lrelu(q.y, a.slope); q.z = lrelu(q.z, a.slope); q.w = lrelu(q.w, a.slope);
+          float4 hi, lo;
+          tc::split_tf32(q.x, hi.x, lo.x); tc::split_tf32(q.y, hi.y, lo.y);
+          tc::split_tf32(q.z, hi.z, lo.z); tc::split_tf32(q.w, hi.w, lo.w);
+          *reinterpret_cast<float4*>(ah + (kc * ROWS + row) * 4) = hi;
+          *reinterpret_cast<float4*>(al + (kc * ROWS + row) * 4) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&a_full[buf]);
+      }
+    } else
     for (int k8 = 0; k8 < nk8; ++k8) {
-      const int buf = k8 & 1;
-      mbar_wait(&a_empty[buf], ((k8 >> 1) & 1) ^ 1);
+      const int buf = k8 % NABUF;
+      mbar_wait(&a_empty[buf], ((k8 / NABUF) & 1) ^ 1);
       float* ah = abuf + buf * Cfg::A_BUF_FLOATS;
-      float* al = ah + 2 * TC_ROWS * 4;
+      float* al = ah + 2 * ROWS * 4;
       // all global loads of a batch are issued before any is consumed (the loop is latency-, not bandwidth-bound)
       constexpr int PB = 5;
       for (int i0 = pt; i0 < items; i0 += 128 * PB) {
@@ -176,8 +285,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
           float4 hi, lo;
           tc::split_tf32(q.x, hi.x, lo.x); tc::split_tf32(q.y, hi.y, lo.y);
           tc::split_tf32(q.z, hi.z, lo.z); tc::split_tf32(q.w, hi.w, lo.w);
-          *reinterpret_cast<float4*>(ah + (kc * TC_ROWS + row) * 4) = hi;
-          *reinterpret_cast<float4*>(al + (kc * TC_ROWS + row) * 4) = lo;
+          *reinterpret_cast<float4*>(ah + (kc * ROWS + row) * 4) = hi;
+          *reinterpret_cast<float4*>(al + (kc * ROWS + row) * 4) = lo;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async) proxy
@@ -192,19 +301,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int t = t0 + mt * 128 + lane_base + lane;
-      const bool ok = t < lim;
+      const bool ok = t < lim && !(a.dbg & 2);
       float* yp = yb + (size_t)t * a.Ntot + n0;
       const float* rp = rb ? rb + (size_t)t * a.Ntot + n0 : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < TN; c0 += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem_d + ((uint32_t)lane_base << 16) + mt * TN + c0, v);
-        if constexpr (Cfg::LOACC) {
-          float lo[32];
-          tc::tmem_ld32(tmem_d + ((uint32_t)lane_base << 16) + (MT + mt) * TN + c0, lo);
+        // everything with latency is issued first: both TMEM reads and the residual / accumulate loads
+        const bool two = Cfg::LOACC && a.passes == 3;
+        uint32_t rm[32], rl[32];
+        tc::tmem_ld32_issue(tmem_d + ((uint32_t)lane_base << 16) + mt * TN + c0, rm);
+        if (two) tc::tmem_ld32_issue(tmem_d + ((uint32_t)lane_base << 16) + (MT + mt) * TN + c0, rl);
+        float4 rq[8], yq[8];
+        if (ok && rp) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += lo[i];
+          for (int q = 0; q < 8; ++q) rq[q] = *reinterpret_cast<const float4*>(rp + c0 + 4 * q);
         }
+        if (ok && a.accumulate) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) yq[q] = *reinterpret_cast<const float4*>(yp + c0 + 4 * q);
+        }
+        tc::tmem_ld_wait(rm);
+        if (two) tc::tmem_ld_wait(rl);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = two ? __uint_as_float(rm[i]) + __uint_as_float(rl[i]) : __uint_as_float(rm[i]);
         if (ok) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -214,16 +334,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
           if (rp) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 rq = *reinterpret_cast<const float4*>(rp + c0 + 4 * q);
-              v[4 * q] += rq.x; v[4 * q + 1] += rq.y; v[4 * q + 2] += rq.z; v[4 * q + 3] += rq.w;
+              v[4 * q] += rq[q].x; v[4 * q + 1] += rq[q].y; v[4 * q + 2] += rq[q].z; v[4 * q + 3] += rq[q].w;
             }
           }
           if (a.accumulate) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 yq = *reinterpret_cast<const float4*>(yp + c0 + 4 * q);
-              v[4 * q] = yq.x + v[4 * q]; v[4 * q + 1] = yq.y + v[4 * q + 1];
-              v[4 * q + 2] = yq.z + v[4 * q + 2]; v[4 * q + 3] = yq.w + v[4 * q + 3];
+              v[4 * q] = yq[q].x + v[4 * q]; v[4 * q + 1] = yq[q].y + v[4 * q + 1];
+              v[4 * q + 2] = yq[q].z + v[4 * q + 2]; v[4 * q + 3] = yq[q].w + v[4 * q + 3];
             }
           }
           if (a.scale != 1.f) {
@@ -239,6 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcconv_kernel(const TcConvArgs 
   }
   tc::fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) tc::tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
 }
 

@@ -55,7 +55,7 @@ def native(request):
     m = get_native(False)
     m.native.set_precision(getattr(request, "param", "fp32"))
     yield m
-    m.native.set_precision("fp32")
+    m.native.set_precision(m.precision)
 
 
 @pytest.fixture(scope="session")
