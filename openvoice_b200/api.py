@@ -261,13 +261,15 @@ class ToneColorConverter(OpenVoiceBaseClass):
         dev = self.device
         if min(len(w) for w in waves) <= (hps.data.filter_length - hop) // 2:
             raise ValueError("audio shorter than the STFT reflect padding")   # torch raises here too
-        # host -> device: one pinned staging buffer, one copy
+        # host -> device: one pinned staging buffer (cached across calls: cudaHostAlloc is slow), one copy
         Lmax = max(len(w) for w in waves)
-        stage = torch.zeros(B, Lmax, dtype=torch.float32).pin_memory()
+        stage = self._pinned("in", B * Lmax).view(B, Lmax)
         for b, w in enumerate(waves):
             stage[b, : len(w)] = torch.from_numpy(w)
+            if len(w) < Lmax:
+                stage[b, len(w):] = 0.0
         wav = stage.to(dev, non_blocking=True)
-        wlen = torch.tensor([len(w) for w in waves], dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+        wlen = torch.tensor([len(w) for w in waves], dtype=torch.int64, device=dev)
         nz = None
         if noise is not None:
             nz = torch.zeros(B, hps.model.inter_channels, Tmax, device=dev, dtype=torch.float32)
@@ -277,11 +279,20 @@ class ToneColorConverter(OpenVoiceBaseClass):
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         # spectrogram + voice_conversion, every item at its own exact length (api.py:148-154)
         o, _ = self.model.native.convert_waveform(wav, wlen, src, tgt, noise=nz, tau=float(tau), seed=seed)
-        host = torch.empty(o.shape, dtype=torch.float32).pin_memory()
+        host = self._pinned("out", o.numel()).view(o.shape)
         host.copy_(o, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         audio = host.numpy()
         return [audio[b, : frames[b] * hop].copy() for b in range(B)]
+
+    def _pinned(self, name, numel):
+        """Grow-only pinned host staging buffers."""
+        cache = self.__dict__.setdefault("_pin_cache", {})
+        buf = cache.get(name)
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(int(numel * 1.25) + 1024, dtype=torch.float32).pin_memory()
+            cache[name] = buf
+        return buf[:numel]
 
     # ------------------------------------------------------------------ watermark (third-party model)
     def add_watermark(self, audio, message):

@@ -90,6 +90,7 @@ struct TcLayer {
 
 struct WNLayers {
   std::vector<ConvLayer> in, rs;
+  std::vector<TcLayer> tc_in, tc_rs;   // tensor-core twins (channels-last)
 };
 
 struct DebugBuf {
@@ -132,6 +133,7 @@ struct ovc_ctx {
   int* d_cond_sel = nullptr;
   int cond_rows_out = 0;
   int cond_off_enc = 0, cond_off_fsrc = 0, cond_off_ftgt = 0, cond_off_dec = 0;
+  int cond_off_enc_tc = 0, cond_off_fsrc_tc = 0, cond_off_ftgt_tc = 0;   // same vectors in the tc kernel's column order
 
   // STFT tables (twiddles exp(-2 pi i m / 1024), periodic hann window)
   float2* d_tw = nullptr;
@@ -226,6 +228,12 @@ static inline int paired_row(int p, int half) {
   return r < 4 ? 4 * q + r : half + 4 * q + (r - 4);
 }
 
+// column order of the tensor-core WN gate: every 32-column group = 16 tanh rows then their 16 sigmoid partners
+static inline int paired_row32(int p, int half) {
+  const int g = p / 32, r = p % 32;
+  return r < 16 ? 16 * g + r : half + 16 * g + (r - 16);
+}
+
 static int dec_variant(int C, int K, int D) {
   const int cls = C >= 128 ? 0 : (C == 64 ? 1 : 2);
   static const int tab[3][3][3] = {
@@ -295,7 +303,8 @@ static int pack_wn(ovc_ctx* c, const std::string& prefix, int n_layers, WNLayers
 template <class WF, class BF>
 static TcLayer pack_tc(ovc_ctx* c, int Ntot, int Cin, int K, int DIL, WF wfun, BF bfun) {
   TcLayer T;
-  T.Cin = Cin; T.Ntot = Ntot; T.K = K; T.DIL = DIL; T.TN = Ntot < 128 ? Ntot : 128;
+  T.Cin = Cin; T.Ntot = Ntot; T.K = K; T.DIL = DIL;
+  T.TN = Ntot % 128 == 0 ? 128 : (Ntot % 64 == 0 ? 64 : 32);   // widest column tile that divides the row
   T.w_off = round_up(c->h_tcw.size(), 64);
   const int slot = 2 * 2 * T.TN * 4;
   c->h_tcw.resize(T.w_off + (size_t)(Ntot / T.TN) * (Cin / 8) * K * slot, 0.f);
@@ -323,6 +332,28 @@ static TcLayer pack_tc(ovc_ctx* c, int Ntot, int Cin, int K, int DIL, WF wfun, B
   return T;
 }
 
+static int pack_wn_tc(ovc_ctx* c, const std::string& prefix, int n_layers, WNLayers* out, std::string* missing) {
+  const int H = 192;
+  for (int i = 0; i < n_layers; ++i) {
+    HostTensor w;
+    const std::string pin = prefix + ".in_layers." + std::to_string(i);
+    if (effective_weight(c, pin, &w, missing)) return -1;
+    out->tc_in.push_back(pack_tc(
+        c, 2 * H, H, 5, 1, [&](int p, int ci, int k) { return w.data[((size_t)paired_row32(p, H) * H + ci) * 5 + k]; },
+        [&](int) { return 0.f; }));   // bias comes per utterance from the cond kernel
+    const std::string prs = prefix + ".res_skip_layers." + std::to_string(i);
+    HostTensor r;
+    if (effective_weight(c, prs, &r, missing)) return -1;
+    const HostTensor* rb = find(c, prs + ".bias");
+    if (!rb) { *missing = prs + ".bias"; return -1; }
+    const int rows = (i < n_layers - 1) ? 2 * H : H;
+    out->tc_rs.push_back(pack_tc(
+        c, rows, H, 1, 1, [&](int p, int ci, int) { return r.data[(size_t)p * H + ci]; },
+        [&](int p) { return rb->data[p]; }));
+  }
+  return 0;
+}
+
 static int finalize(ovc_ctx* c) {
   const ovc_hparams& hp = c->hp;
   const int H = 192, S = hp.spec_channels, G = hp.gin_channels;
@@ -345,7 +376,9 @@ static int finalize(ovc_ctx* c) {
                            [&](int p) { return b->data[p]; }, H, 1, H);
     c->enc_pre16 = c->enc_pre;            // same packing, 16-byte cp.async when the spectrogram pitch allows it
     c->enc_pre16.variant = V_FLOW_PRE;
-    if (pack_wn(c, "enc_q.enc", 16, &c->enc_wn, &miss)) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    c->enc_wn = WNLayers();
+    if (pack_wn(c, "enc_q.enc", 16, &c->enc_wn, &miss) || pack_wn_tc(c, "enc_q.enc", 16, &c->enc_wn, &miss))
+      return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
     NEED(pw, "enc_q.proj.weight");
     NEED(pb, "enc_q.proj.bias");
     if (pw->shape[0] != 2 * H || pw->shape[1] != H) return fail(OVC_ERR_INVALID, "enc_q.proj.weight has the wrong shape");
@@ -366,7 +399,9 @@ static int finalize(ovc_ctx* c) {
         c, V_FLOW_PRE, H, 96,
         [&](int r, int ci, int) { return w->data[(size_t)r * 96 + (flipped ? 95 - ci : ci)]; },
         [&](int r) { return b->data[r]; }, H, 1, H);
-    if (pack_wn(c, p + ".enc", 4, &c->flow_wn[f], &miss)) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    c->flow_wn[f] = WNLayers();
+    if (pack_wn(c, p + ".enc", 4, &c->flow_wn[f], &miss) || pack_wn_tc(c, p + ".enc", 4, &c->flow_wn[f], &miss))
+      return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
     NEED(pw, p + ".post.weight");
     NEED(pb, p + ".post.bias");
     if (pw->shape[0] != 96 || pw->shape[1] != H) return fail(OVC_ERR_INVALID, "%s.post.weight has the wrong shape (mean_only couplings only)", p.c_str());
@@ -447,7 +482,7 @@ static int finalize(ovc_ctx* c) {
   std::vector<float> cbias;
   {
     std::vector<float> cw;
-    auto add_wn = [&](const std::string& prefix, int n_layers, int first_row, int selv, bool add_matrix) -> int {
+    auto add_wn = [&](const std::string& prefix, int n_layers, int first_row, int selv, bool add_matrix, bool tc_order = false) -> int {
       HostTensor w;
       if (effective_weight(c, prefix + ".cond_layer", &w, &miss)) return -1;
       const HostTensor* cb = find(c, prefix + ".cond_layer.bias");
@@ -458,7 +493,7 @@ static int finalize(ovc_ctx* c) {
         const HostTensor* ib = find(c, prefix + ".in_layers." + std::to_string(l) + ".bias");
         if (!ib) { miss = prefix + ".in_layers." + std::to_string(l) + ".bias"; return -1; }
         for (int p = 0; p < 2 * H; ++p) {
-          const int o = paired_row(p, H);
+          const int o = tc_order ? paired_row32(p, H) : paired_row(p, H);
           wrow.push_back(first_row + l * 2 * H + o);
           sel.push_back(selv);
           cbias.push_back(cb->data[l * 2 * H + o] + ib->data[o]);
@@ -475,6 +510,17 @@ static int finalize(ovc_ctx* c) {
     c->cond_off_ftgt = (int)wrow.size();
     for (int f = 0; f < 4; ++f)
       if (add_wn("flow.flows." + std::to_string(2 * f) + ".enc", 4, 16 * 2 * H + f * 4 * 2 * H, 2, false))
+        return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    // the same conditioning vectors once more in the tensor-core kernel's column order
+    c->cond_off_enc_tc = (int)wrow.size();
+    if (add_wn("enc_q.enc", 16, 0, hp.zero_g ? 0 : 1, false, true)) return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    c->cond_off_fsrc_tc = (int)wrow.size();
+    for (int f = 0; f < 4; ++f)
+      if (add_wn("flow.flows." + std::to_string(2 * f) + ".enc", 4, 16 * 2 * H + f * 4 * 2 * H, 1, false, true))
+        return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
+    c->cond_off_ftgt_tc = (int)wrow.size();
+    for (int f = 0; f < 4; ++f)
+      if (add_wn("flow.flows." + std::to_string(2 * f) + ".enc", 4, 16 * 2 * H + f * 4 * 2 * H, 2, false, true))
         return fail(OVC_ERR_MISSING, "checkpoint tensor '%s' is missing or mis-shaped", miss.c_str());
     c->cond_off_dec = (int)wrow.size();
     NEED(dw, "dec.cond.weight");
@@ -662,16 +708,28 @@ static const char* variant_name(int v) {
   return v == V_TC128 ? "TC3_N128" : v == V_TC64 ? "TC3_N64" : v == V_TC32 ? "TC3_N32" : "TRANSPOSE";
 }
 
-// one generator conv on the tensor cores (3xTF32), channels-last in/out.  t_len / mul are in INPUT steps.
+// one conv on the tensor cores (3xTF32 / TF32), channels-last in/out.  t_len / mul are in INPUT steps.
+struct TcExtra {
+  int epi = 0;                    // 0 linear, 1 WN gate, 2 WN res/skip
+  const float* bias = nullptr;    // override (per-utterance conditioning vector), with stride
+  long long bias_bs = 0;
+  float* s = nullptr;             // skip accumulator (EPI 2)
+  int split = 0, first = 0;
+  int y_ld = 0;                   // output row width when it differs from Ntot
+  bool use_lens_frames = false;   // limits are the frame lengths (enc/flow) instead of the generator lengths
+};
 static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const float* res, int t_len, int mul, float slope,
-                     float scale, int accumulate, int family) {
+                     float scale, int accumulate, int family, const TcExtra& ex = TcExtra()) {
   TcConvArgs a{};
+  const int y_ld = ex.y_ld ? ex.y_ld : T.Ntot;
   a.x = x; a.x_bs = (long long)T.Cin * r.P * mul;
   a.w = r.c->d_tcw + T.w_off;
-  a.bias = r.c->d_tcw + T.b_off;
-  a.y = y; a.y_bs = (long long)T.Ntot * r.P * mul;
+  a.bias = ex.bias ? ex.bias : r.c->d_tcw + T.b_off; a.bias_bs = ex.bias_bs;
+  a.y = y; a.y_bs = (long long)y_ld * r.P * mul; a.y_ld = y_ld;
   a.r = res;
-  a.lens = r.glens; a.tmax = r.Tmax; a.mul = mul;
+  a.s = ex.s; a.s_bs = a.y_bs;
+  a.epi = ex.epi; a.split = ex.split; a.first = ex.first;
+  a.lens = ex.use_lens_frames ? r.lens : r.glens; a.tmax = r.Tmax; a.mul = mul;
   a.Cin = T.Cin; a.Ntot = T.Ntot; a.K = T.K; a.DIL = T.DIL;
   a.slope = slope; a.scale = scale; a.accumulate = accumulate;
   a.passes = r.c->precision == 2 ? 1 : 3;
@@ -696,8 +754,8 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   CK(cudaGetLastError());
   r.c->launches++;
   const double units = (double)r.B * t_len;
-  const int eff_k = family == 1 ? T.K : 2;   // polyphase transposed conv: 2 of the 3 packed taps are non-zero per row
-  TRY(prof_end(r, T.TN == 128 ? V_TC128 : T.TN == 64 ? V_TC64 : V_TC32, family, 2.0 * T.Cin * T.Ntot * eff_k * units,
+  const int eff_k = family == 2 ? 2 : T.K;   // polyphase transposed conv: 2 of the 3 packed taps are non-zero per row
+  TRY(prof_end(r, T.TN == 128 ? V_TC128 : T.TN == 64 ? V_TC64 : V_TC32, family == 1 ? 1 : 0, 2.0 * T.Cin * T.Ntot * eff_k * units,
                4.0 * (T.Cin + T.Ntot) * units));
   return OVC_OK;
 }
@@ -739,6 +797,25 @@ static int run_wn(Run& r, const WNLayers& wn, float* x, float* skip, float* acts
   return OVC_OK;
 }
 
+// the same stack on the tensor cores: x, acts, skip live channels-last inside the stack; h comes in and the
+// output leaves in the [C][T] layout of the small FFMA kernels around it (pre / proj / post)
+static int run_wn_tc(Run& r, const WNLayers& wn, float* x, float* skip, float* acts, float* x_cl, float* skip_cl,
+                     const float* cond_tc, int cond_bs) {
+  const int P = r.P, T = r.Tmax;
+  const int n = (int)wn.tc_in.size();
+  TRY(launch_transpose(r, x, x_cl, 192, P));
+  for (int i = 0; i < n; ++i) {
+    TcExtra g;
+    g.epi = 1; g.bias = cond_tc + (size_t)i * 384; g.bias_bs = cond_bs; g.y_ld = 192; g.use_lens_frames = true;
+    TRY(launch_tc(r, wn.tc_in[i], x_cl, acts, nullptr, T, 1, 1.f, 1.f, 0, 0, g));
+    TcExtra q;
+    q.epi = 2; q.s = skip_cl; q.split = (i < n - 1) ? 192 : 0; q.first = (i == 0); q.y_ld = 192; q.use_lens_frames = true;
+    TRY(launch_tc(r, wn.tc_rs[i], acts, x_cl, nullptr, T, 1, 1.f, 1.f, 0, 0, q));
+  }
+  TRY(launch_transpose(r, skip_cl, skip, P, 192));
+  return OVC_OK;
+}
+
 static int run_flow(Run& r, const WsLayout& W, float* ws, bool reverse, const float* cond_all) {
   ovc_ctx* c = r.c;
   const int P = r.P, T = r.Tmax;
@@ -759,7 +836,12 @@ static int run_flow(Run& r, const WsLayout& W, float* ws, bool reverse, const fl
     a.lens_in = r.lens; a.lens_out = r.lens; a.mul_in = 1; a.mul_out = 1;
     a.slope = 1.f; a.scale = 1.f;
     TRY(launch(r, c->flow_pre[f], a, T));
-    TRY(run_wn(r, c->flow_wn[f], x, skip, acts, cond_all + sect + f * 4 * 384, c->cond_rows_out));
+    if (c->precision >= 1) {
+      const int sect_tc = reverse ? c->cond_off_ftgt_tc : c->cond_off_fsrc_tc;
+      TRY(run_wn_tc(r, c->flow_wn[f], x, skip, acts, ws + W.bufA, ws + W.bufB, cond_all + sect_tc + f * 4 * 384, c->cond_rows_out));
+    } else {
+      TRY(run_wn(r, c->flow_wn[f], x, skip, acts, cond_all + sect + f * 4 * 384, c->cond_rows_out));
+    }
     // post + coupling update of x1 in place                                (modules.py:441-454)
     ConvArgs b{};
     b.x = skip; b.x_bs = bs; b.x_pitch = P;
@@ -826,7 +908,12 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
     const bool aligned = (spec_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(spec) & 15) == 0);
     TRY(launch(r, aligned ? c->enc_pre16 : c->enc_pre, a, Tmax));
     TRY(tap(r, "enc.pre", ws + W.x, 192, Tmax, P));
-    TRY(run_wn(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, cond + c->cond_off_enc, c->cond_rows_out));
+    if (c->precision >= 1) {
+      TRY(run_wn_tc(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, ws + W.bufA, ws + W.bufB, cond + c->cond_off_enc_tc,
+                    c->cond_rows_out));
+    } else {
+      TRY(run_wn(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, cond + c->cond_off_enc, c->cond_rows_out));
+    }
     TRY(tap(r, "enc.wn", ws + W.skip, 192, Tmax, P));
     ConvArgs p{};
     p.x = ws + W.skip; p.x_bs = bs192; p.x_pitch = P;
@@ -884,7 +971,7 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
       const int cout = cin / 2, up_out = up * s;
       const int Tlen = Tmax * up_out, pitch_out = P * up_out;
       char nm[32];
-      TRY(launch_tc(r, c->tc_ups[i], stage_in, bufA, nullptr, Tmax * up, up, 0.1f, 1.f, 0, 0));
+      TRY(launch_tc(r, c->tc_ups[i], stage_in, bufA, nullptr, Tmax * up, up, 0.1f, 1.f, 0, 2));
       snprintf(nm, sizeof nm, "dec.ups%d", i);
       TRY(tap_cl(nm, bufA, cout, Tlen, pitch_out));
       for (int j = 0; j < 3; ++j)

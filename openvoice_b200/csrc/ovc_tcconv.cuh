@@ -25,9 +25,12 @@ namespace ovc {
 struct TcConvArgs {
   const float* x; long long x_bs;     // [B][Lpitch][Cin]
   const float* w;                      // packed [n_tiles][Cin/8][K][2 (hi|lo)][2 (k chunk)][TN][4]
-  const float* bias;                   // [Ntot]
-  float* y; long long y_bs;            // [B][Lpitch][Ntot]
+  const float* bias; long long bias_bs; // [Ntot] (+ b * bias_bs: per-utterance speaker-conditioning bias of the WN gate)
+  float* y; long long y_bs; int y_ld;  // [B][Lpitch][y_ld]
   const float* r;                      // residual, same geometry as y (nullable)
+  float* s; long long s_bs;            // EPI 2: skip accumulator [B][Lpitch][y_ld]
+  int epi;                             // 0 linear (bias, residual, accumulate, scale) | 1 WN gate | 2 WN res/skip
+  int split; int first;                // EPI 2: columns < split update y (x += rs), the rest go to s[col - split] (= / +=)
   const long long* lens; int tmax; int mul;   // valid steps = min(tmax, lens[b]) * mul   (lens NULL -> tmax)
   int Cin; int Ntot; int K; int DIL;   // Ntot = output row width (C for a ResBlock conv, stride*Cout for a polyphase transposed conv)
   float slope; float scale; int accumulate;
@@ -298,12 +301,14 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
     const int lane_base = (warp & 3) * 32;
     float* yb = a.y + (size_t)b * a.y_bs;
     const float* rb = a.r ? a.r + (size_t)b * a.y_bs : nullptr;
+    float* sb = a.s ? a.s + (size_t)b * a.s_bs : nullptr;
+    const float* bias = a.bias + (size_t)b * a.bias_bs;
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int t = t0 + mt * 128 + lane_base + lane;
       const bool ok = t < lim && !(a.dbg & 2);
-      float* yp = yb + (size_t)t * a.Ntot + n0;
-      const float* rp = rb ? rb + (size_t)t * a.Ntot + n0 : nullptr;
+      float* yp = yb + (size_t)t * a.y_ld + n0;
+      const float* rp = rb ? rb + (size_t)t * a.y_ld + n0 : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < TN; c0 += 32) {
         // everything with latency is issued first: both TMEM reads and the residual / accumulate loads
@@ -312,6 +317,40 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
         tc::tmem_ld32_issue(tmem_d + ((uint32_t)lane_base << 16) + mt * TN + c0, rm);
         if (two) tc::tmem_ld32_issue(tmem_d + ((uint32_t)lane_base << 16) + (MT + mt) * TN + c0, rl);
         float4 rq[8], yq[8];
+        if (a.epi != 0) {
+          // ---- WaveNet epilogues (modules.py:185-210), channels-last
+          tc::tmem_ld_wait(rm);
+          if (two) tc::tmem_ld_wait(rl);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = (two ? __uint_as_float(rm[i]) + __uint_as_float(rl[i]) : __uint_as_float(rm[i])) + bias[n0 + c0 + i];
+          if (!ok) continue;
+          const int col = n0 + c0;
+          if (a.epi == 1) {
+            // columns [0,16) of the group: tanh inputs of 16 channels, [16,32): their sigmoid partners
+            float* op = yb + (size_t)t * a.y_ld + (col >> 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = tanhf(v[4 * q + e]) * sigmoidf_acc(v[16 + 4 * q + e]);
+              *reinterpret_cast<float4*>(op + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          } else {
+            const bool to_x = col < a.split;          // uniform per 32-column group (split is a multiple of 32)
+            float* op = to_x ? yb + (size_t)t * a.y_ld + col : sb + (size_t)t * a.y_ld + (col - a.split);
+            const bool add = to_x || !a.first;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (add) cur = *reinterpret_cast<const float4*>(op + 4 * q);
+              cur.x += v[4 * q]; cur.y += v[4 * q + 1]; cur.z += v[4 * q + 2]; cur.w += v[4 * q + 3];
+              *reinterpret_cast<float4*>(op + 4 * q) = cur;
+            }
+          }
+          continue;
+        }
         if (ok && rp) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) rq[q] = *reinterpret_cast<const float4*>(rp + c0 + 4 * q);
@@ -328,7 +367,7 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
         if (ok) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 bq = *reinterpret_cast<const float4*>(a.bias + n0 + c0 + 4 * q);
+            const float4 bq = *reinterpret_cast<const float4*>(bias + n0 + c0 + 4 * q);
             v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
           if (rp) {
