@@ -132,6 +132,13 @@ OVC_API int ovc_convert_waveform(ovc_ctx* ctx, const float* wav, const int64_t* 
                                  const float* g_src, const float* g_tgt, const float* noise, uint64_t seed,
                                  float tau, float* o_hat, int64_t* frames, void* stream);
 
+/* Tone-colour embedding of extract_se (row f2): ReferenceEncoder.forward (openvoice/models.py:339-359; call site
+ * openvoice/api.py:130) on device -- LayerNorm over frequency, 6 x (Conv2d 3x3 s2 + ReLU), GRU(128) last state,
+ * Linear.  Needs the checkpoint's ref_enc.* tensors (OVC_ERR_MISSING otherwise).
+ *   spec  [N, spec_channels, T] magnitude spectrogram as written by ovc_spectrogram (all N items T frames)
+ *   out   [N, gin]                                                                                          */
+OVC_API int ovc_reference_encoder(ovc_ctx* ctx, const float* spec, int N, int T, float* out, void* stream);
+
 /* Arithmetic of the generator's ResBlock convolutions (90 % of the FLOPs):
  *   0 (default)  fp32 FFMA2 on the CUDA cores
  *   1            split-precision 3xTF32 on the 5th-gen tensor cores (tcgen05 + TMEM): every product is

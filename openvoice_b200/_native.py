@@ -18,7 +18,7 @@ EXPORTS = (
     "ovc_abi_version", "ovc_last_error", "ovc_create", "ovc_destroy", "ovc_load_tensor",
     "ovc_finalize_weights", "ovc_workspace_floats", "ovc_voice_conversion", "ovc_last_launch_count",
     "ovc_profile_enable", "ovc_profile_read", "ovc_profile_detail", "ovc_debug_enable", "ovc_debug_fetch",
-    "ovc_spectrogram", "ovc_convert_waveform", "ovc_set_precision",
+    "ovc_spectrogram", "ovc_convert_waveform", "ovc_set_precision", "ovc_reference_encoder",
 )
 
 
@@ -67,6 +67,7 @@ def load_library(path: Optional[str] = None):
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ovc_last_launch_count.argtypes = [C.c_void_p]
     lib.ovc_set_precision.argtypes = [C.c_void_p, C.c_int]
+    lib.ovc_reference_encoder.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ovc_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.ovc_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -248,6 +249,19 @@ class NativeConverter:
             C.c_void_p(st.cuda_stream))
         _check(self.lib, rc, "ovc_convert_waveform")
         return o, frames
+
+    def reference_encoder(self, spec, stream=None):
+        """spec [N, S, T] f32 cuda (ovc_spectrogram layout) -> tone-colour embedding [N, gin]
+        (ReferenceEncoder.forward, openvoice/models.py:339-359)."""
+        import torch
+        assert spec.is_cuda and spec.dtype == torch.float32 and spec.is_contiguous() and spec.dim() == 3
+        N, S, T = spec.shape
+        out = torch.empty(N, self.hp.gin_channels, device=spec.device, dtype=torch.float32)
+        st = stream if stream is not None else torch.cuda.current_stream(spec.device)
+        rc = self.lib.ovc_reference_encoder(self.handle, C.c_void_p(spec.data_ptr()), N, T, C.c_void_p(out.data_ptr()),
+                                            C.c_void_p(st.cuda_stream))
+        _check(self.lib, rc, "ovc_reference_encoder")
+        return out
 
     @property
     def last_launch_count(self) -> int:

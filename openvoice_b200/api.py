@@ -94,7 +94,7 @@ class NativeSynthesizer:
         self.precision = precision or os.environ.get("OVC_PRECISION", "tf32x3")
         self.native.set_precision(self.precision)
         self.spec_channels = hps.data.filter_length // 2 + 1
-        self.ref_enc = ReferenceEncoder(self.spec_channels, int(getattr(hps.model, "gin_channels", 256)))
+        self.ref_enc = ReferenceEncoder(self.native, self.spec_channels, int(getattr(hps.model, "gin_channels", 256)))
         self._expected = hot_path_keys(hps) + ref_enc_keys()
 
     # nn.Module-ish surface used by callers of the reference
@@ -116,7 +116,6 @@ class NativeSynthesizer:
         unexpected = sorted(provided - expected)
         self.native.load_state_dict(state_dict)
         self.native.finalize()          # raises OvcError naming the first missing hot-path key
-        self.ref_enc.load_state_dict(state_dict, self.device)
         if strict and (missing or unexpected):
             raise RuntimeError(f"missing keys {missing}, unexpected keys {unexpected}")
         return missing, unexpected
@@ -198,7 +197,7 @@ class ToneColorConverter(OpenVoiceBaseClass):
             y = torch.from_numpy(audio_ref).to(self.device).unsqueeze(0).contiguous()
             n = torch.tensor([y.shape[1]], dtype=torch.int64, device=self.device)
             y, _ = self.model.native.spectrogram(y, n)          # = spectrogram_torch (api.py:126-128)
-            g = self.model.ref_enc(y.transpose(1, 2)).unsqueeze(-1)
+            g = self.model.native.reference_encoder(y).unsqueeze(-1)   # = model.ref_enc(y.transpose(1, 2)) (api.py:130)
             gs.append(g.detach())
         gs = torch.stack(gs).mean(0)
         if se_save_path is not None:

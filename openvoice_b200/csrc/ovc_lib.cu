@@ -16,6 +16,7 @@
 #include "../../include/ovc.h"
 #include "ovc_small.cuh"
 #include "ovc_tcconv.cuh"
+#include "ovc_refenc.cuh"
 #include "ovc_variants.h"
 
 namespace ovc {
@@ -138,6 +139,13 @@ struct ovc_ctx {
   // STFT tables (twiddles exp(-2 pi i m / 1024), periodic hann window)
   float2* d_tw = nullptr;
   float* d_win = nullptr;
+
+  // ReferenceEncoder (extract_se): offsets into d_w, own scratch
+  bool has_refenc = false;
+  size_t re_conv_w[6] = {0}, re_conv_b[6] = {0}, re_wih = 0, re_whh = 0, re_bih = 0, re_bhh = 0, re_pw = 0, re_pb = 0,
+         re_lng = 0, re_lnb = 0;
+  float* d_re = nullptr;
+  size_t re_floats = 0;
 
   // workspace
   float* d_ws = nullptr;
@@ -269,7 +277,7 @@ static int validate_hparams(const ovc_hparams* hp) {
 }
 
 static bool key_is_hot(const std::string& k) {
-  return k.rfind("enc_q.", 0) == 0 || k.rfind("flow.", 0) == 0 || k.rfind("dec.", 0) == 0;
+  return k.rfind("enc_q.", 0) == 0 || k.rfind("flow.", 0) == 0 || k.rfind("dec.", 0) == 0 || k.rfind("ref_enc.", 0) == 0;
 }
 
 static int pack_wn(ovc_ctx* c, const std::string& prefix, int n_layers, WNLayers* out, std::string* missing) {
@@ -540,6 +548,31 @@ static int finalize(ovc_ctx* c) {
     c->cond_b_off = round_up(c->h_w.size(), 64);
     c->h_w.resize(c->cond_b_off + cbias.size());
     std::copy(cbias.begin(), cbias.end(), c->h_w.begin() + c->cond_b_off);
+  }
+  // ---- ReferenceEncoder (optional: only extract_se needs it; models.py:301-338)
+  c->has_refenc = false;
+  if (find(c, "ref_enc.proj.weight")) {
+    auto put = [&](const std::vector<float>& v) { size_t o = round_up(c->h_w.size(), 64); c->h_w.resize(o + v.size()); std::copy(v.begin(), v.end(), c->h_w.begin() + o); return o; };
+    static const int filt[7] = {1, 32, 32, 64, 64, 128, 128};
+    for (int i = 0; i < 6; ++i) {
+      const std::string q = "ref_enc.convs." + std::to_string(i);
+      WEFF(cw, q);
+      NEED(cb, q + ".bias");
+      if (cw.shape.size() != 4 || cw.shape[0] != filt[i + 1] || cw.shape[1] != filt[i] || cw.shape[2] != 3 || cw.shape[3] != 3)
+        return fail(OVC_ERR_INVALID, "%s weight has the wrong shape", q.c_str());
+      c->re_conv_w[i] = put(cw.data);
+      c->re_conv_b[i] = put(cb->data);
+    }
+    NEED(wih, "ref_enc.gru.weight_ih_l0"); NEED(whh, "ref_enc.gru.weight_hh_l0");
+    NEED(bih, "ref_enc.gru.bias_ih_l0"); NEED(bhh, "ref_enc.gru.bias_hh_l0");
+    NEED(rpw, "ref_enc.proj.weight"); NEED(rpb, "ref_enc.proj.bias");
+    NEED(lng, "ref_enc.layernorm.weight"); NEED(lnb, "ref_enc.layernorm.bias");
+    if (wih->shape[0] != 384 || whh->shape[0] != 384 || whh->shape[1] != 128 || rpw->shape[0] != G || rpw->shape[1] != 128 ||
+        lng->shape[0] != S)
+      return fail(OVC_ERR_INVALID, "ref_enc.* tensors have the wrong shape");
+    c->re_wih = put(wih->data); c->re_whh = put(whh->data); c->re_bih = put(bih->data); c->re_bhh = put(bhh->data);
+    c->re_pw = put(rpw->data); c->re_pb = put(rpb->data); c->re_lng = put(lng->data); c->re_lnb = put(lnb->data);
+    c->has_refenc = true;
   }
 #undef NEED
 #undef WEFF
@@ -1107,6 +1140,7 @@ void ovc_destroy(ovc_ctx* c) {
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
   if (c->d_tcw) cudaFree(c->d_tcw);
+  if (c->d_re) cudaFree(c->d_re);
   if (c->d_tw) cudaFree(c->d_tw);
   if (c->d_win) cudaFree(c->d_win);
   for (auto& e : c->ev) cudaEventDestroy(e);
@@ -1196,6 +1230,59 @@ int ovc_convert_waveform(ovc_ctx* c, const float* wav, const int64_t* wav_length
   const int rc = run_vc(c, spec, W.P, fr, g_src, g_tgt, noise, seed, tau, B, Tmax, 1, o_hat, nullptr, nullptr, nullptr, st);
   c->launches += 1;
   return rc;
+}
+
+int ovc_reference_encoder(ovc_ctx* c, const float* spec, int N, int T, float* out, void* stream) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  if (!c->finalized) return fail(OVC_ERR_STATE, "ovc_finalize_weights has not been called");
+  if (!c->has_refenc) return fail(OVC_ERR_MISSING, "the checkpoint had no ref_enc.* tensors");
+  if (!spec || !out || N < 1 || T < 1) return fail(OVC_ERR_INVALID, "bad argument to ovc_reference_encoder");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int F = c->hp.spec_channels, G = c->hp.gin_channels;
+  static const int filt[7] = {1, 32, 32, 64, 64, 128, 128};
+  int H[7], W[7];
+  H[0] = T; W[0] = F;
+  size_t maxact = (size_t)N * T * F;
+  for (int i = 0; i < 6; ++i) {
+    H[i + 1] = (H[i] - 1) / 2 + 1; W[i + 1] = (W[i] - 1) / 2 + 1;
+    maxact = std::max(maxact, (size_t)N * filt[i + 1] * H[i + 1] * W[i + 1]);
+  }
+  if ((size_t)filt[6] * W[6] != 1152 && false) return fail(OVC_ERR_INVALID, "unexpected GRU input width");
+  const size_t gi_floats = (size_t)N * H[6] * 384;
+  const size_t need = 2 * round_up(maxact, 64) + round_up(gi_floats, 64);
+  if (need > c->re_floats) {
+    CK(cudaStreamSynchronize(st));
+    if (c->d_re) CK(cudaFree(c->d_re));
+    c->d_re = nullptr; c->re_floats = 0;
+    CK(cudaMalloc(&c->d_re, need * sizeof(float)));
+    c->re_floats = need;
+  }
+  float* a0 = c->d_re;
+  float* a1 = a0 + round_up(maxact, 64);
+  float* gi = a1 + round_up(maxact, 64);
+  {
+    const int warps = N * T;
+    refenc_layernorm_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(spec, c->d_w + c->re_lng, c->d_w + c->re_lnb, a0, N, F, T);
+    CK(cudaGetLastError());
+  }
+  float* cur = a0; float* nxt = a1;
+  for (int i = 0; i < 6; ++i) {
+    const long long total = (long long)N * filt[i + 1] * H[i + 1] * W[i + 1];
+    refenc_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cur, c->d_w + c->re_conv_w[i], c->d_w + c->re_conv_b[i], nxt, N,
+                                                                        filt[i], H[i], W[i], filt[i + 1], H[i + 1], W[i + 1]);
+    CK(cudaGetLastError());
+    std::swap(cur, nxt);
+  }
+  {
+    const long long warps = (long long)N * H[6] * 384;
+    refenc_gru_in_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(cur, c->d_w + c->re_wih, c->d_w + c->re_bih, gi, N, 128,
+                                                                              H[6], W[6], 384);
+    CK(cudaGetLastError());
+    refenc_gru_kernel<<<N, 128, 0, st>>>(gi, c->d_w + c->re_whh, c->d_w + c->re_bhh, c->d_w + c->re_pw, c->d_w + c->re_pb, out, H[6], G);
+    CK(cudaGetLastError());
+  }
+  return OVC_OK;
 }
 
 int ovc_set_precision(ovc_ctx* c, int mode) {

@@ -401,36 +401,40 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
 }
 
 // conv_post on channels-last input: y[b, t] = tanh(sum_{k<7, ci<C} w[ci, k] * lrelu_0.01(x[b, t+k-3, ci]))
-// (models.py:287-289).  One thread per output sample; the 7 input rows (128 B each) are shared through L1.
+// (models.py:287-289).  HBM-bound (132 B per sample): a CTA stages 256+6 rows with coalesced 16-byte loads into a
+// transposed, conflict-free shared tile (leaky_relu applied once), then one thread per output sample.
 template <int C>
 __global__ void __launch_bounds__(256) conv_post_cl_kernel(const float* __restrict__ x, long long x_bs,
                                                            const float* __restrict__ w, float* __restrict__ y,
                                                            long long y_bs, int y_len, const long long* lens, int tmax,
                                                            int mul) {
-  __shared__ float ws[7][C];   // transposed: [k][ci]
+  constexpr int TB = 256, ROWS = TB + 6, LD = ROWS + 3;   // LD odd: conflict-free transposed stores
+  __shared__ float ws[7][C];
+  __shared__ float xs[C][LD];
   for (int i = threadIdx.x; i < C * 7; i += blockDim.x) ws[i % 7][i / 7] = w[i];
-  __syncthreads();
   const int b = blockIdx.y;
   const int lim = (lens ? (int)min((long long)tmax, lens[b]) : tmax) * mul;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t0 = blockIdx.x * TB;
+  const float* xb = x + (size_t)b * x_bs;
+  for (int idx = threadIdx.x; idx < ROWS * (C / 4); idx += blockDim.x) {
+    const int row = idx / (C / 4), q = idx % (C / 4);
+    const int tt = t0 - 3 + row;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt >= 0 && tt < lim) v = *reinterpret_cast<const float4*>(xb + (size_t)tt * C + 4 * q);
+    xs[4 * q + 0][row] = v.x > 0.f ? v.x : 0.01f * v.x;
+    xs[4 * q + 1][row] = v.y > 0.f ? v.y : 0.01f * v.y;
+    xs[4 * q + 2][row] = v.z > 0.f ? v.z : 0.01f * v.z;
+    xs[4 * q + 3][row] = v.w > 0.f ? v.w : 0.01f * v.w;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
   if (t >= y_len) return;
   float acc = 0.f;
   if (t < lim) {
-    const float* xb = x + (size_t)b * x_bs;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int tt = t + k - 3;
-      if (tt < 0 || tt >= lim) continue;
-      const float4* row = reinterpret_cast<const float4*>(xb + (size_t)tt * C);
-#pragma unroll
-      for (int q = 0; q < C / 4; ++q) {
-        const float4 v = row[q];
-        acc = fmaf(ws[k][4 * q + 0], v.x > 0.f ? v.x : 0.01f * v.x, acc);
-        acc = fmaf(ws[k][4 * q + 1], v.y > 0.f ? v.y : 0.01f * v.y, acc);
-        acc = fmaf(ws[k][4 * q + 2], v.z > 0.f ? v.z : 0.01f * v.z, acc);
-        acc = fmaf(ws[k][4 * q + 3], v.w > 0.f ? v.w : 0.01f * v.w, acc);
-      }
-    }
+    for (int k = 0; k < 7; ++k)
+#pragma unroll 8
+      for (int ci = 0; ci < C; ++ci) acc = fmaf(ws[k][ci], xs[ci][threadIdx.x + k], acc);
     acc = tanhf(acc);
   }
   y[(size_t)b * y_bs + t] = acc;
