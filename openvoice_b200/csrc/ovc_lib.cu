@@ -590,6 +590,8 @@ static int finalize(ovc_ctx* c) {
   CK(cudaFuncSetAttribute(tcconv_kernel<128, TC_CL128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<128>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tcconv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<64>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tcconv_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<32>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_narrow_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<64>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_narrow_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<32>::SMEM_BYTES));
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
   CK(cudaMalloc(&c->d_cond_wrow, wrow.size() * sizeof(int)));
@@ -782,8 +784,18 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
     at[0].val.clusterDim.x = TC_CL128; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     CK(cudaLaunchKernelEx(&cfg, tcconv_kernel<128, TC_CL128>, a));
-  } else if (T.TN == 64) tcconv_kernel<64, 1><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, r.st>>>(a);
-  else tcconv_kernel<32, 1><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, r.st>>>(a);
+  } else {
+    static const bool persistent = !(getenv("OVC_TC_NARROW") && atoi(getenv("OVC_TC_NARROW")) == 0);
+    if (persistent) {
+      // one CTA per SM walks the (utterance, 512-step tile) list; column tiles (if any) on grid.y
+      const int n_tt = (int)grid.x, total = n_tt * r.B;
+      const int per_col = std::max(1, r.c->sm_count / (int)grid.y);
+      dim3 pg((unsigned)std::min(total, per_col), grid.y, 1);
+      if (T.TN == 64) tcconv_narrow_kernel<64><<<pg, TCN_THREADS, TcnCfg<64>::SMEM_BYTES, r.st>>>(a, n_tt, total);
+      else tcconv_narrow_kernel<32><<<pg, TCN_THREADS, TcnCfg<32>::SMEM_BYTES, r.st>>>(a, n_tt, total);
+    } else if (T.TN == 64) tcconv_kernel<64, 1><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, r.st>>>(a);
+    else tcconv_kernel<32, 1><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, r.st>>>(a);
+  }
   CK(cudaGetLastError());
   r.c->launches++;
   const double units = (double)r.B * t_len;

@@ -99,6 +99,108 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Epilogue of one CTA tile (MT x 128 steps x TN columns): TMEM -> registers -> fused ops -> global.
+// Warp w may read TMEM lanes [32*(w%4), +32); tmem_d = main accumulators, low-order ones (LOACC) MT*TN columns after.
+template <int TN, int MT, bool LOACC>
+__device__ __forceinline__ void tc_epilogue(const TcConvArgs& a, uint32_t tmem_d, int b, int t0, int n0, int lim, int warp,
+                                            int lane) {
+    const int lane_base = (warp & 3) * 32;
+    float* yb = a.y + (size_t)b * a.y_bs;
+    const float* rb = a.r ? a.r + (size_t)b * a.y_bs : nullptr;
+    float* sb = a.s ? a.s + (size_t)b * a.s_bs : nullptr;
+    const float* bias = a.bias + (size_t)b * a.bias_bs;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int t = t0 + mt * 128 + lane_base + lane;
+      const bool ok = t < lim && !(a.dbg & 2);
+      float* yp = yb + (size_t)t * a.y_ld + n0;
+      const float* rp = rb ? rb + (size_t)t * a.y_ld + n0 : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        // everything with latency is issued first: both TMEM reads and the residual / accumulate loads
+        const bool two = LOACC && a.passes == 3;
+        uint32_t rm[32], rl[32];
+        tc::tmem_ld32_issue(tmem_d + ((uint32_t)lane_base << 16) + mt * TN + c0, rm);
+        if (two) tc::tmem_ld32_issue(tmem_d + ((uint32_t)lane_base << 16) + (MT + mt) * TN + c0, rl);
+        float4 rq[8], yq[8];
+        if (a.epi != 0) {
+          // ---- WaveNet epilogues (modules.py:185-210), channels-last
+          tc::tmem_ld_wait(rm);
+          if (two) tc::tmem_ld_wait(rl);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = (two ? __uint_as_float(rm[i]) + __uint_as_float(rl[i]) : __uint_as_float(rm[i])) + bias[n0 + c0 + i];
+          if (!ok) continue;
+          const int col = n0 + c0;
+          if (a.epi == 1) {
+            // columns [0,16) of the group: tanh inputs of 16 channels, [16,32): their sigmoid partners
+            float* op = yb + (size_t)t * a.y_ld + (col >> 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = tanhf(v[4 * q + e]) * sigmoidf_acc(v[16 + 4 * q + e]);
+              *reinterpret_cast<float4*>(op + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          } else {
+            const bool to_x = col < a.split;          // uniform per 32-column group (split is a multiple of 32)
+            float* op = to_x ? yb + (size_t)t * a.y_ld + col : sb + (size_t)t * a.y_ld + (col - a.split);
+            const bool add = to_x || !a.first;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (add) cur = *reinterpret_cast<const float4*>(op + 4 * q);
+              cur.x += v[4 * q]; cur.y += v[4 * q + 1]; cur.z += v[4 * q + 2]; cur.w += v[4 * q + 3];
+              *reinterpret_cast<float4*>(op + 4 * q) = cur;
+            }
+          }
+          continue;
+        }
+        if (ok && rp) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rq[q] = *reinterpret_cast<const float4*>(rp + c0 + 4 * q);
+        }
+        if (ok && a.accumulate) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) yq[q] = *reinterpret_cast<const float4*>(yp + c0 + 4 * q);
+        }
+        tc::tmem_ld_wait(rm);
+        if (two) tc::tmem_ld_wait(rl);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = two ? __uint_as_float(rm[i]) + __uint_as_float(rl[i]) : __uint_as_float(rm[i]);
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(bias + n0 + c0 + 4 * q);
+            v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+          }
+          if (rp) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              v[4 * q] += rq[q].x; v[4 * q + 1] += rq[q].y; v[4 * q + 2] += rq[q].z; v[4 * q + 3] += rq[q].w;
+            }
+          }
+          if (a.accumulate) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              v[4 * q] = yq[q].x + v[4 * q]; v[4 * q + 1] = yq[q].y + v[4 * q + 1];
+              v[4 * q + 2] = yq[q].z + v[4 * q + 2]; v[4 * q + 3] = yq[q].w + v[4 * q + 3];
+            }
+          }
+          if (a.scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= a.scale;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(yp + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+    }
+}
+
 template <int TN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(const TcConvArgs a) {
   using Cfg = TcCfg<TN>;
@@ -298,105 +400,212 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
     // epilogue: warp w may read TMEM lanes [32*(w%4), +32)
     mbar_wait(acc_full, 0);
     tc::fence_after();
-    const int lane_base = (warp & 3) * 32;
-    float* yb = a.y + (size_t)b * a.y_bs;
-    const float* rb = a.r ? a.r + (size_t)b * a.y_bs : nullptr;
-    float* sb = a.s ? a.s + (size_t)b * a.s_bs : nullptr;
-    const float* bias = a.bias + (size_t)b * a.bias_bs;
-#pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      const int t = t0 + mt * 128 + lane_base + lane;
-      const bool ok = t < lim && !(a.dbg & 2);
-      float* yp = yb + (size_t)t * a.y_ld + n0;
-      const float* rp = rb ? rb + (size_t)t * a.y_ld + n0 : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        // everything with latency is issued first: both TMEM reads and the residual / accumulate loads
-        const bool two = Cfg::LOACC && a.passes == 3;
-        uint32_t rm[32], rl[32];
-        tc::tmem_ld32_issue(tmem_d + ((uint32_t)lane_base << 16) + mt * TN + c0, rm);
-        if (two) tc::tmem_ld32_issue(tmem_d + ((uint32_t)lane_base << 16) + (MT + mt) * TN + c0, rl);
-        float4 rq[8], yq[8];
-        if (a.epi != 0) {
-          // ---- WaveNet epilogues (modules.py:185-210), channels-last
-          tc::tmem_ld_wait(rm);
-          if (two) tc::tmem_ld_wait(rl);
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            v[i] = (two ? __uint_as_float(rm[i]) + __uint_as_float(rl[i]) : __uint_as_float(rm[i])) + bias[n0 + c0 + i];
-          if (!ok) continue;
-          const int col = n0 + c0;
-          if (a.epi == 1) {
-            // columns [0,16) of the group: tanh inputs of 16 channels, [16,32): their sigmoid partners
-            float* op = yb + (size_t)t * a.y_ld + (col >> 1);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = tanhf(v[4 * q + e]) * sigmoidf_acc(v[16 + 4 * q + e]);
-              *reinterpret_cast<float4*>(op + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          } else {
-            const bool to_x = col < a.split;          // uniform per 32-column group (split is a multiple of 32)
-            float* op = to_x ? yb + (size_t)t * a.y_ld + col : sb + (size_t)t * a.y_ld + (col - a.split);
-            const bool add = to_x || !a.first;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (add) cur = *reinterpret_cast<const float4*>(op + 4 * q);
-              cur.x += v[4 * q]; cur.y += v[4 * q + 1]; cur.z += v[4 * q + 2]; cur.w += v[4 * q + 3];
-              *reinterpret_cast<float4*>(op + 4 * q) = cur;
-            }
-          }
-          continue;
-        }
-        if (ok && rp) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) rq[q] = *reinterpret_cast<const float4*>(rp + c0 + 4 * q);
-        }
-        if (ok && a.accumulate) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) yq[q] = *reinterpret_cast<const float4*>(yp + c0 + 4 * q);
-        }
-        tc::tmem_ld_wait(rm);
-        if (two) tc::tmem_ld_wait(rl);
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = two ? __uint_as_float(rm[i]) + __uint_as_float(rl[i]) : __uint_as_float(rm[i]);
-        if (ok) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bq = *reinterpret_cast<const float4*>(bias + n0 + c0 + 4 * q);
-            v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
-          }
-          if (rp) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              v[4 * q] += rq[q].x; v[4 * q + 1] += rq[q].y; v[4 * q + 2] += rq[q].z; v[4 * q + 3] += rq[q].w;
-            }
-          }
-          if (a.accumulate) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              v[4 * q] = yq[q].x + v[4 * q]; v[4 * q + 1] = yq[q].y + v[4 * q + 1];
-              v[4 * q + 2] = yq[q].z + v[4 * q + 2]; v[4 * q + 3] = yq[q].w + v[4 * q + 3];
-            }
-          }
-          if (a.scale != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= a.scale;
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(yp + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-      }
-    }
+    tc_epilogue<TN, MT, Cfg::LOACC>(a, tmem_d, b, t0, n0, lim, warp, lane);
   }
   tc::fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // peers may still multicast into / arrive on this CTA's shared memory
+  if (warp == 1) tc::tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tcconv_narrow_kernel: persistent variant for the narrow layers (TN = 32 / 64 output columns per CTA).
+// Per 512-step tile these layers have only 1-5 us of MMA work, so the one-tile-per-CTA kernel above is dominated
+// by fixed costs (barrier init, TMEM allocation, first-load latency, a serial epilogue).  Here one CTA per SM
+// loops over tiles: barriers / TMEM live for the whole launch, the layer's weights stay resident in shared
+// memory when they fit (C = 32: <= 88 KB; otherwise the ring streams them per tile), A staging runs ahead across
+// tile boundaries, and the epilogue of tile i (own 4 warps, second TMEM accumulator set) overlaps the MMAs of
+// tile i+1.  Warps: 0 TMA, 1-2 MMA issuers, 3-6 A producers, 7-10 epilogue.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TCN_THREADS = 352;
+
+template <int TN>
+struct TcnCfg {
+  static constexpr int MT = 4;
+  static constexpr int ROWS = MT * 128 + 64;
+  static constexpr int NABUF = 2;
+  static constexpr int RING = TN == 32 ? 44 : 16;                 // weight slots: 88 KB (TN 32) / 64 KB (TN 64)
+  static constexpr int A_BUF_FLOATS = 2 * 2 * ROWS * 4;
+  static constexpr int B_SLOT_FLOATS = 2 * 2 * TN * 4;
+  static constexpr size_t SMEM_BYTES = 1024 + sizeof(float) * (NABUF * A_BUF_FLOATS + RING * B_SLOT_FLOATS);
+  static constexpr uint32_t TMEM_COLS = 2 * MT * TN;              // two accumulator sets: 256 / 512
+};
+
+template <int TN>
+__global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcConvArgs a, int n_tt, int total) {
+  using Cfg = TcnCfg<TN>;
+  constexpr int MT = Cfg::MT, ROWS = Cfg::ROWS, NABUF = Cfg::NABUF, RING = Cfg::RING;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* a_full = bars, *a_empty = bars + NABUF, *b_full = bars + 2 * NABUF, *b_empty = b_full + RING,
+            *acc_full = b_empty + RING, *acc_empty = acc_full + 2;
+  static_assert((2 * NABUF + 2 * RING + 4) * 8 + 8 <= 1024, "barrier area");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* abuf = reinterpret_cast<float*>(smem_raw + 1024);
+  float* bring = abuf + NABUF * Cfg::A_BUF_FLOATS;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * TN;
+  const int H = (a.K - 1) / 2 * a.DIL;
+  const int rows = MT * 128 + 2 * H;
+  const int nk8 = a.Cin / 8;
+  const int n_slots = nk8 * a.K;
+  const bool resident = n_slots <= RING;
+  const uint32_t SLOT_BYTES = (a.passes == 3 ? Cfg::B_SLOT_FLOATS : Cfg::B_SLOT_FLOATS / 2) * sizeof(float);
+
+  if (tid == 0) {
+    for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 2); }
+    for (int i = 0; i < RING; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  // every role walks the same tile sequence
+#define TCN_FOR_TILES                                                                                   \
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {                                        \
+    const int b = tile / n_tt, t0 = (tile % n_tt) * (MT * 128);                                         \
+    const int lim = (a.lens ? (int)min((long long)a.tmax, a.lens[b]) : a.tmax) * a.mul;                 \
+    if (t0 >= lim) continue;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weights
+    if (lane == 0) {
+      const float* wt = a.w + (size_t)blockIdx.y * n_slots * Cfg::B_SLOT_FLOATS;
+      if (resident) {
+        for (int it = 0; it < n_slots; ++it) {
+          mbar_expect_tx(&b_full[it], SLOT_BYTES);
+          tma_bulk_g2s(bring + it * Cfg::B_SLOT_FLOATS, wt + (size_t)it * Cfg::B_SLOT_FLOATS, SLOT_BYTES, &b_full[it]);
+        }
+      } else {
+        int slot = 0;
+        uint32_t phase = 1;
+        TCN_FOR_TILES
+          (void)b; (void)lim;
+          for (int it = 0; it < n_slots; ++it) {
+            mbar_wait(&b_empty[slot], phase);
+            mbar_expect_tx(&b_full[slot], SLOT_BYTES);
+            tma_bulk_g2s(bring + slot * Cfg::B_SLOT_FLOATS, wt + (size_t)it * Cfg::B_SLOT_FLOATS, SLOT_BYTES, &b_full[slot]);
+            if (++slot == RING) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------ MMA issuers (each owns 2 of the 4 MMA tiles)
+    if (lane == 0) {
+      const int mt_lo = (warp - 1) * 2, mt_hi = mt_lo + 2;
+      const uint32_t idesc = tc::make_idesc_tf32(128, TN);
+      constexpr uint32_t LBO_A = ROWS * 16, LBO_B = TN * 16, SBO = 128;
+      constexpr uint32_t A_LO16 = (2 * ROWS * 16) >> 4, B_LO16 = (2 * TN * 16) >> 4, SLOT16 = (Cfg::B_SLOT_FLOATS * 4) >> 4;
+      const uint64_t a_proto = tc::make_desc(0, LBO_A, SBO), b_proto = tc::make_desc(0, LBO_B, SBO);
+      const uint64_t b_ring = b_proto + (tc::smem_addr(bring) >> 4);
+      const uint32_t dil = (uint32_t)a.DIL;
+      const bool three = a.passes == 3;
+      int slot = 0, ka = 0, n = 0;
+      uint32_t bphase = 0;
+      TCN_FOR_TILES
+        (void)b; (void)lim;
+        const int set = n & 1;
+        mbar_wait(&acc_empty[set], ((n >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator set
+        tc::fence_after();
+        const uint32_t acc = tmem_d + set * (MT * TN);
+        bool first = true;
+        if (resident) slot = 0;
+        for (int k8 = 0; k8 < nk8; ++k8, ++ka) {
+          const int buf = ka & (NABUF - 1);
+          mbar_wait(&a_full[buf], (ka / NABUF) & 1);
+          tc::fence_after();
+          uint64_t a_cur = a_proto + (tc::smem_addr(abuf + buf * Cfg::A_BUF_FLOATS) >> 4);
+          for (int tap = 0; tap < a.K; ++tap) {
+            if (!resident || n == 0) {
+              mbar_wait(&b_full[slot], resident ? 0u : bphase);
+              tc::fence_after();
+            }
+            const uint64_t bd_hi = b_ring + (uint32_t)slot * SLOT16, bd_lo = bd_hi + B_LO16;
+#pragma unroll
+            for (int mt = mt_lo; mt < mt_hi; ++mt) {
+              const uint64_t ad_hi = a_cur + mt * 128, ad_lo = ad_hi + A_LO16;
+              const uint32_t d = acc + mt * TN;
+              tc::mma_tf32(d, ad_hi, bd_hi, idesc, !first);
+              if (three) {
+                tc::mma_tf32(d, ad_lo, bd_hi, idesc, true);
+                tc::mma_tf32(d, ad_hi, bd_lo, idesc, true);
+              }
+            }
+            first = false;
+            if (!resident) tc::mma_commit(&b_empty[slot]);
+            a_cur += dil;
+            if (++slot == RING) { slot = 0; bphase ^= 1; }
+          }
+          tc::mma_commit(&a_empty[buf]);
+        }
+        tc::mma_commit(&acc_full[set]);
+        ++n;
+      }
+    }
+  } else if (warp >= 3 && warp <= 6) {
+    // ------------------------------------------------------------ A producers (run ahead across tiles)
+    const int pt = tid - 96;
+    const int items = rows * 2;
+    int ka = 0;
+    TCN_FOR_TILES
+      const float* xb = a.x + (size_t)b * a.x_bs;
+      for (int k8 = 0; k8 < nk8; ++k8, ++ka) {
+        const int buf = ka & (NABUF - 1);
+        mbar_wait(&a_empty[buf], ((ka / NABUF) & 1) ^ 1);
+        float* ah = abuf + buf * Cfg::A_BUF_FLOATS;
+        float* al = ah + 2 * ROWS * 4;
+        constexpr int PB = 5;
+        for (int i0 = pt; i0 < items; i0 += 128 * PB) {
+          float4 v[PB];
+#pragma unroll
+          for (int u = 0; u < PB; ++u) {
+            const int i = i0 + 128 * u;
+            const int row = i >> 1, kc = i & 1;
+            const int t = t0 - H + row;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < items && t >= 0 && t < lim) v[u] = *reinterpret_cast<const float4*>(xb + (size_t)t * a.Cin + k8 * 8 + kc * 4);
+          }
+#pragma unroll
+          for (int u = 0; u < PB; ++u) {
+            const int i = i0 + 128 * u;
+            if (i >= items) break;
+            const int row = i >> 1, kc = i & 1;
+            float4 q = v[u];
+            q.x = lrelu(q.x, a.slope); q.y = lrelu(q.y, a.slope); q.z = lrelu(q.z, a.slope); q.w = lrelu(q.w, a.slope);
+            float4 hi, lo;
+            tc::split_tf32(q.x, hi.x, lo.x); tc::split_tf32(q.y, hi.y, lo.y);
+            tc::split_tf32(q.z, hi.z, lo.z); tc::split_tf32(q.w, hi.w, lo.w);
+            *reinterpret_cast<float4*>(ah + (kc * ROWS + row) * 4) = hi;
+            *reinterpret_cast<float4*>(al + (kc * ROWS + row) * 4) = lo;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&a_full[buf]);
+      }
+    }
+  } else if (warp >= 7) {
+    // ------------------------------------------------------------ epilogue (overlaps the next tile's MMAs)
+    int n = 0;
+    TCN_FOR_TILES
+      const int set = n & 1;
+      mbar_wait(&acc_full[set], (n >> 1) & 1);
+      tc::fence_after();
+      tc_epilogue<TN, MT, false>(a, tmem_d + set * (MT * TN), b, t0, n0, lim, warp, lane);
+      tc::fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
+      ++n;
+    }
+  }
+#undef TCN_FOR_TILES
+  tc::fence_before();
+  __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
 }
 
