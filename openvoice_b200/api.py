@@ -294,42 +294,39 @@ class ToneColorConverter(OpenVoiceBaseClass):
         return buf[:numel]
 
     # ------------------------------------------------------------------ watermark (third-party model)
+    _WM_CHUNK = 16000      # samples per watermarked chunk
+    _WM_STRIDE = 32000     # chunk n starts at n * 32000 (openvoice/api.py:169-171)
+
+    def _wm_chunks(self, audio, count):
+        """Yield (index, slice) of the first ``count`` watermark chunks; a short chunk ends the walk."""
+        for n in range(count):
+            sl = slice(n * self._WM_STRIDE, n * self._WM_STRIDE + self._WM_CHUNK)
+            yield n, sl, len(audio[sl]) == self._WM_CHUNK
+
     def add_watermark(self, audio, message):
-        """openvoice/api.py:162-184 (wavmark encoder on 16000-sample chunks at 0 and 32000)."""
+        """Embed ``message`` with the wavmark model, 32 bits per 16000-sample chunk, chunks 32000 samples apart
+        (behaviour of openvoice/api.py:162-184, incl. the "Audio too short" early stop).  No model -> no-op."""
         if self.watermark_model is None:
             return audio
-        device = self.device
-        bits = utils.string_to_bits(message).reshape(-1)
-        n_repeat = len(bits) // 32
-        K = 16000
-        coeff = 2
-        for n in range(n_repeat):
-            trunck = audio[(coeff * n) * K: (coeff * n + 1) * K]
-            if len(trunck) != K:
+        payload = utils.string_to_bits(message).reshape(-1)
+        for n, sl, full in self._wm_chunks(audio, len(payload) // 32):
+            if not full:
                 print("Audio too short, fail to add watermark")
                 break
-            message_npy = bits[n * 32: (n + 1) * 32]
             with torch.no_grad():
-                signal = torch.FloatTensor(trunck).to(device)[None]
-                message_tensor = torch.FloatTensor(message_npy).to(device)[None]
-                signal_wmd_tensor = self.watermark_model.encode(signal, message_tensor)
-                signal_wmd_npy = signal_wmd_tensor.detach().cpu().squeeze()
-            audio[(coeff * n) * K: (coeff * n + 1) * K] = signal_wmd_npy
+                sig = torch.as_tensor(audio[sl], dtype=torch.float32, device=self.device)[None]
+                bits = torch.as_tensor(payload[32 * n: 32 * (n + 1)], dtype=torch.float32, device=self.device)[None]
+                audio[sl] = self.watermark_model.encode(sig, bits).detach().cpu().squeeze()
         return audio
 
     def detect_watermark(self, audio, n_repeat):
-        """openvoice/api.py:186-201."""
-        bits = []
-        K = 16000
-        coeff = 2
-        for n in range(n_repeat):
-            trunck = audio[(coeff * n) * K: (coeff * n + 1) * K]
-            if len(trunck) != K:
+        """Decode ``n_repeat`` chunks back to text (openvoice/api.py:186-201); "Fail" when the audio is too short."""
+        rows = []
+        for n, sl, full in self._wm_chunks(audio, n_repeat):
+            if not full:
                 print("Audio too short, fail to detect watermark")
                 return "Fail"
             with torch.no_grad():
-                signal = torch.FloatTensor(trunck).to(self.device).unsqueeze(0)
-                message_decoded_npy = (self.watermark_model.decode(signal) >= 0.5).int().detach().cpu().numpy().squeeze()
-            bits.append(message_decoded_npy)
-        bits = np.stack(bits).reshape(-1, 8)
-        return utils.bits_to_string(bits)
+                sig = torch.as_tensor(audio[sl], dtype=torch.float32, device=self.device)[None]
+                rows.append((self.watermark_model.decode(sig) >= 0.5).int().detach().cpu().numpy().squeeze())
+        return utils.bits_to_string(np.stack(rows).reshape(-1, 8))

@@ -529,6 +529,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcC
             const uint64_t bd_hi = b_ring + (uint32_t)slot * SLOT16, bd_lo = bd_hi + B_LO16;
 #pragma unroll
             for (int mt = mt_lo; mt < mt_hi; ++mt) {
+              if (a.dbg & 4) continue;
               const uint64_t ad_hi = a_cur + mt * 128, ad_lo = ad_hi + A_LO16;
               const uint32_t d = acc + mt * TN;
               tc::mma_tf32(d, ad_hi, bd_hi, idesc, !first);
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcC
   } else if (warp >= 3 && warp <= 6) {
     // ------------------------------------------------------------ A producers (run ahead across tiles)
     const int pt = tid - 96;
-    const int items = rows * 2;
+    const int items = (a.dbg & 1) ? 0 : rows * 2;
     int ka = 0;
     TCN_FOR_TILES
       const float* xb = a.x + (size_t)b * a.x_bs;
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcC
         mbar_wait(&a_empty[buf], ((ka / NABUF) & 1) ^ 1);
         float* ah = abuf + buf * Cfg::A_BUF_FLOATS;
         float* al = ah + 2 * ROWS * 4;
-        constexpr int PB = 5;
+        constexpr int PB = 9;   // all of a thread's loads for one chunk in flight at once (<= 1124 items / 128 threads)
         for (int i0 = pt; i0 < items; i0 += 128 * PB) {
           float4 v[PB];
 #pragma unroll

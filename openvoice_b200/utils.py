@@ -5,40 +5,27 @@ import json
 import numpy as np
 
 
-class HParams:
-    """Attribute tree over a (nested) dict; behaves like the reference's HParams
-    (openvoice/utils.py:14-43): item and attribute access, ``in``, ``len``, keys/items/values."""
+class HParams(dict):
+    """Nested config tree with attribute *and* item access (``hps.data.hop_length``, ``hps["model"]``,
+    ``"zero_g" in hps.model``, ``len``, ``keys/items/values``) -- the behaviour callers of the reference's
+    ``utils.HParams`` (openvoice/utils.py:14-43) rely on, implemented as a dict subclass."""
 
-    def __init__(self, **kwargs):
-        for k, v in kwargs.items():
-            self[k] = HParams(**v) if isinstance(v, dict) else v
+    def __init__(self, **entries):
+        super().__init__()
+        for key, value in entries.items():
+            self[key] = HParams(**value) if isinstance(value, dict) else value
 
-    def keys(self):
-        return self.__dict__.keys()
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
 
-    def items(self):
-        return self.__dict__.items()
-
-    def values(self):
-        return self.__dict__.values()
-
-    def __len__(self):
-        return len(self.__dict__)
-
-    def __getitem__(self, key):
-        return getattr(self, key)
-
-    def __setitem__(self, key, value):
-        setattr(self, key, value)
-
-    def __contains__(self, key):
-        return key in self.__dict__
-
-    def __repr__(self):
-        return repr(self.__dict__)
+    def __setattr__(self, name, value):
+        self[name] = value
 
     def to_dict(self):
-        return {k: (v.to_dict() if isinstance(v, HParams) else v) for k, v in self.__dict__.items()}
+        return {k: (v.to_dict() if isinstance(v, HParams) else v) for k, v in self.items()}
 
 
 def get_hparams_from_file(config_path):

@@ -119,6 +119,37 @@ def test_audio_loader(tmp_path):
     assert np.array_equal(np.load(tmp_path / "o.npy"), x)
 
 
+def test_watermark_chunking_roundtrip():
+    """add_watermark / detect_watermark chunk walk (16000-sample chunks every 32000 samples, 32 bits each,
+    "too short" handling -- openvoice/api.py:162-201) with a stand-in codec model."""
+    from openvoice_b200 import utils
+    from openvoice_b200.api import ToneColorConverter
+
+    class FakeWM:                                   # hides the 32 bits in the first 32 samples of a chunk
+        def encode(self, sig, bits):
+            out = sig.clone()
+            out[:, :32] = bits * 0.5 + 0.25
+            return out
+
+        def decode(self, sig):
+            return (sig[:, :32] - 0.25) / 0.5
+
+    conv = ToneColorConverter.__new__(ToneColorConverter)     # no GPU needed for this logic
+    conv.device = "cpu"
+    conv.watermark_model = FakeWM()
+    audio = np.zeros(32000 * 1 + 16000, dtype=np.float32)     # room for chunks 0 and 1
+    out = conv.add_watermark(audio.copy(), "@MyShell")
+    assert conv.detect_watermark(out, 2) == "@MyShell"
+    assert np.count_nonzero(out[16000:32000]) == 0            # only the chunk windows are touched
+    short = np.zeros(20000, dtype=np.float32)
+    out2 = conv.add_watermark(short.copy(), "@MyShell")       # second chunk does not fit: first is still written
+    assert np.count_nonzero(out2[:32]) > 0
+    assert conv.detect_watermark(out2, 2) == "Fail"
+    conv.watermark_model = None
+    assert conv.add_watermark(short, "x") is short
+    assert utils.string_to_bits("@MyShell").shape == (8, 8)
+
+
 def test_lpt_shard_balances_and_covers():
     from openvoice_b200.distributed import lpt_shard
     costs = [10, 1, 7, 3, 3, 9, 2, 8]
