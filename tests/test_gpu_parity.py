@@ -203,6 +203,36 @@ def test_spectrogram_kernel(native):
         assert float(spec[b, :, n // 256:].abs().max()) == 0.0 if n // 256 < L // 256 else True
 
 
+def test_full_size_batch_properties(tmp_path, synthetic_sd):
+    """BASELINE-size workload (32 x 10 s clips) through the public API: finite, in [-1, 1], right lengths;
+    the same torch seed reproduces the batch bit for bit; an item of the batch equals its solo conversion
+    (tau = 0 so no noise is involved); ragged tails are not touched."""
+    from openvoice_b200.api import ToneColorConverter
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps(O.DEFAULT_HPARAMS))
+    conv = ToneColorConverter(str(cfg), device="cuda:0", enable_watermark=False)
+    conv.model.load_state_dict(synthetic_sd)
+    rng = np.random.default_rng(7)
+    lens = [220500] * 30 + [220500 - 4321, 66150]
+    wavs = [(0.5 * (2 * rng.random(n, dtype=np.float32) - 1)).astype(np.float32) for n in lens]
+    gen = torch.Generator().manual_seed(5)
+    src = 0.1 * torch.randn(1, 256, 1, generator=gen)
+    tgt = 0.1 * torch.randn(1, 256, 1, generator=gen)
+    torch.manual_seed(123)
+    a = conv.convert_batch(wavs, src, tgt, tau=0.3, max_batch=32)
+    torch.manual_seed(123)
+    b = conv.convert_batch(wavs, src, tgt, tau=0.3, max_batch=32)
+    for x, y, n in zip(a, b, lens):
+        assert x.shape == (256 * (n // 256),) and np.isfinite(x).all() and np.abs(x).max() <= 1.0
+        assert np.array_equal(x, y)
+    c = conv.convert_batch(wavs, src, tgt, tau=0.0, max_batch=32)
+    for i in (0, 30, 31):
+        assert np.array_equal(conv.convert(wavs[i], src, tgt, tau=0.0), c[i])
+    torch.manual_seed(124)
+    d = conv.convert_batch(wavs[:2], src, tgt, tau=0.3)
+    assert not np.array_equal(d[0], a[0])            # a different seed draws different noise
+
+
 def test_api_convert_matches_reference_golden(tmp_path, synthetic_sd):
     """ToneColorConverter.convert end to end (waveform -> spectrogram -> VC -> samples) against
     the real reference's convert() output."""
