@@ -53,15 +53,25 @@ constexpr int TC_CL128 = OVC_TC_CL;      // CTAs per cluster of the wide variant
 template <int TN>
 struct TcCfg {
   // accumulation steps = 3 * Cin/8 * K: only the wide layers (C >= 128 -> TN = 128) are long enough to drift
-  static constexpr bool LOACC = TN == 128;
-  static constexpr int MT = TN == 128 ? 2 : 4;                   // MMA tiles (of 128 steps) per CTA
+  // Two ways to keep the low-order terms out of the long accumulation (wide variant only):
+  //   LOACC    : their own TMEM accumulator (costs half the TMEM -> MT = 2, twice the weight re-streaming)
+  //   TWOSWEEP : sweep 0 accumulates all a_lo*b_hi + a_hi*b_lo terms (tiny magnitudes, no drift), sweep 1 adds the
+  //              a_hi*b_hi terms on top -- one accumulator, MT = 4, weights re-streamed 1.5x per 512 steps instead of
+  //              2x per 256.  Same accuracy (3.1e-5), but measured SLOWER (wide kernels 116 vs 75 ms per call): the A
+  //              tiles are produced twice and the short hi*hi sweep is issue / producer bound.  Kept for reference.
+#ifndef OVC_TC_TWOSWEEP
+#define OVC_TC_TWOSWEEP 0
+#endif
+  static constexpr bool TWOSWEEP = TN == 128 && OVC_TC_TWOSWEEP;
+  static constexpr bool LOACC = TN == 128 && !TWOSWEEP;
+  static constexpr int MT = LOACC ? 2 : 4;                       // MMA tiles (of 128 steps) per CTA
   static constexpr int ROWS = MT * 128 + 64;                     // staged rows per A buffer (tile + 2*25 halo, padded)
   // the producers are latency-bound (ncu: long_scoreboard ~70 %): the 1-CTA/SM wide variant gets a deep pipeline,
   // the narrow ones run 2 CTAs per SM and hide latency that way
   static constexpr int NABUF = 2;                                // A stages (8 input channels each)
   // weight streaming is latency-bound: throughput = ring bytes / L2 latency, so the wide variant (1 CTA per SM)
   // spends all the shared memory it can on the ring (ablation: A production is hidden, the ring is not)
-  static constexpr int SLOTS = TN == 128 ? 20 : 8;               // weight ring depth
+  static constexpr int SLOTS = TN == 128 ? (TWOSWEEP ? 14 : 20) : 8;   // weight ring depth
   static constexpr int A_BUF_FLOATS = 2 * 2 * ROWS * 4;          // [hi|lo][k chunk][row][4]
   static constexpr int B_SLOT_FLOATS = 2 * 2 * TN * 4;           // [hi|lo][k chunk][n][4]
   // raw fp32 landing stages for the producers' cp.async prefetch (rows x 8 channels), RAWD chunks ahead
@@ -229,6 +239,8 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
   const int H = (a.K - 1) / 2 * a.DIL;
   const int rows = MT * 128 + 2 * H;
   const int nk8 = a.Cin / 8;
+  const int n_sweeps = (Cfg::TWOSWEEP && a.passes == 3) ? 2 : 1;
+  const int nq = n_sweeps * nk8;            // flattened (sweep, 8-channel chunk) sequence
 
   if (tid == 0) {
     for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], TC_NISS); }
@@ -247,20 +259,24 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
     // ------------------------------------------------------------ weight producer (TMA bulk)
     if (lane == 0) {
       const float* wt = a.w + (size_t)blockIdx.y * nk8 * a.K * Cfg::B_SLOT_FLOATS;
-      // a slot is [hi | lo]; single-pass TF32 needs (and fetches) only the first half
-      const uint32_t BYTES = (a.passes == 3 ? Cfg::B_SLOT_FLOATS : Cfg::B_SLOT_FLOATS / 2) * sizeof(float);
-      const int PART = (int)(BYTES / sizeof(float)) / CL;
+      // a slot is [hi | lo]; the hi*hi sweep and single-pass TF32 need (and fetch) only the first half
       const int n_slots = nk8 * a.K;
       int slot = 0;
       uint32_t phase = 1;   // the first pass over the ring finds every slot free
-      for (int it = 0; it < n_slots; ++it) {
-        mbar_wait(&b_empty[slot], phase);
-        mbar_expect_tx(&b_full[slot], BYTES);
-        float* dst = bring + slot * Cfg::B_SLOT_FLOATS;
-        if (CL == 1) tma_bulk_g2s(dst, wt, BYTES, &b_full[slot]);
-        else tma_bulk_g2s_mcast(dst + crank * PART, wt + crank * PART, BYTES / CL, &b_full[slot], CMASK);
-        wt += Cfg::B_SLOT_FLOATS;
-        if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+      for (int sweep = 0; sweep < n_sweeps; ++sweep) {
+        const bool full = a.passes == 3 && (!Cfg::TWOSWEEP || sweep == 0);
+        const uint32_t BYTES = (full ? Cfg::B_SLOT_FLOATS : Cfg::B_SLOT_FLOATS / 2) * sizeof(float);
+        const int PART = (int)(BYTES / sizeof(float)) / CL;
+        const float* wp = wt;
+        for (int it = 0; it < n_slots; ++it) {
+          mbar_wait(&b_empty[slot], phase);
+          mbar_expect_tx(&b_full[slot], BYTES);
+          float* dst = bring + slot * Cfg::B_SLOT_FLOATS;
+          if (CL == 1) tma_bulk_g2s(dst, wp, BYTES, &b_full[slot]);
+          else tma_bulk_g2s_mcast(dst + crank * PART, wp + crank * PART, BYTES / CL, &b_full[slot], CMASK);
+          wp += Cfg::B_SLOT_FLOATS;
+          if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1 || warp == 6) {
@@ -282,9 +298,10 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
       int slot = 0;
       uint32_t bphase = 0;
       bool first = true;
-      for (int k8 = 0; k8 < nk8; ++k8) {
-        const int buf = k8 & (NABUF - 1);
-        if (active) mbar_wait(&a_full[buf], (k8 / NABUF) & 1);
+      for (int q = 0; q < nq; ++q) {
+        const int sweep = q >= nk8 ? 1 : 0;
+        const int buf = q & (NABUF - 1);
+        if (active) mbar_wait(&a_full[buf], (q / NABUF) & 1);
         tc::fence_after();
         uint64_t a_cur = a_proto + (tc::smem_addr(abuf + buf * Cfg::A_BUF_FLOATS) >> 4);
         for (int tap = 0; tap < a.K; ++tap) {
@@ -298,10 +315,19 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
               const uint64_t ad_hi = a_cur + mt * 128, ad_lo = ad_hi + A_LO16;
               const uint32_t d = tmem_d + mt * TN;
               const uint32_t dl = Cfg::LOACC ? tmem_d + (MT + mt) * TN : d;   // low-order terms: own accumulator
-              tc::mma_tf32(d, ad_hi, bd_hi, idesc, !first);
-              if (three) {
-                tc::mma_tf32(dl, ad_lo, bd_hi, idesc, Cfg::LOACC ? !first : true);
-                tc::mma_tf32(dl, ad_hi, bd_lo, idesc, true);
+              if (Cfg::TWOSWEEP && three) {
+                if (sweep == 0) {              // low-order terms first, at their own scale
+                  tc::mma_tf32(d, ad_lo, bd_hi, idesc, !first);
+                  tc::mma_tf32(d, ad_hi, bd_lo, idesc, true);
+                } else {
+                  tc::mma_tf32(d, ad_hi, bd_hi, idesc, true);
+                }
+              } else {
+                tc::mma_tf32(d, ad_hi, bd_hi, idesc, !first);
+                if (three) {
+                  tc::mma_tf32(dl, ad_lo, bd_hi, idesc, Cfg::LOACC ? !first : true);
+                  tc::mma_tf32(dl, ad_hi, bd_lo, idesc, true);
+                }
               }
             }
           }
@@ -325,8 +351,9 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
       // conversion (lrelu, hi/lo split, operand layout) then runs shared -> shared on data this thread staged
       constexpr int NST = Cfg::RAWD + 1;
       float* raw = bring + SLOTS * Cfg::B_SLOT_FLOATS;
-      auto stage = [&](int k8) {
-        float* dst = raw + (k8 % NST) * Cfg::RAW_FLOATS;
+      auto stage = [&](int q) {
+        const int k8 = q >= nk8 ? q - nk8 : q;
+        float* dst = raw + (q % NST) * Cfg::RAW_FLOATS;
         for (int i = pt; i < ((a.dbg & 1) ? 0 : items); i += 128) {
           const int row = i >> 1, kc = i & 1;
           const int t = t0 - H + row;
@@ -336,19 +363,19 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      for (int k8 = 0; k8 < Cfg::RAWD; ++k8) {
-        if (k8 < nk8) stage(k8);
+      for (int q = 0; q < Cfg::RAWD; ++q) {
+        if (q < nq) stage(q);
         else asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      for (int k8 = 0; k8 < nk8; ++k8) {
-        if (k8 + Cfg::RAWD < nk8) stage(k8 + Cfg::RAWD);
+      for (int q = 0; q < nq; ++q) {
+        if (q + Cfg::RAWD < nq) stage(q + Cfg::RAWD);
         else asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count uniform
         asm volatile("cp.async.wait_group %0;" ::"n"(Cfg::RAWD) : "memory");
-        const int buf = k8 % NABUF;
-        mbar_wait(&a_empty[buf], ((k8 / NABUF) & 1) ^ 1);
+        const int buf = q % NABUF;
+        mbar_wait(&a_empty[buf], ((q / NABUF) & 1) ^ 1);
         float* ah = abuf + buf * Cfg::A_BUF_FLOATS;
         float* al = ah + 2 * ROWS * 4;
-        const float* src = raw + (k8 % NST) * Cfg::RAW_FLOATS;
+        const float* src = raw + (q % NST) * Cfg::RAW_FLOATS;
         for (int i = pt; i < ((a.dbg & 1) ? 0 : items); i += 128) {
           const int row = i >> 1, kc = i & 1;
           float4 q = *reinterpret_cast<const float4*>(src + i * 4);
@@ -363,9 +390,10 @@ __global__ void __launch_bounds__(TC_THREADS, TN == 128 ? 1 : 2) tcconv_kernel(c
         mbar_arrive(&a_full[buf]);
       }
     } else
-    for (int k8 = 0; k8 < nk8; ++k8) {
-      const int buf = k8 % NABUF;
-      mbar_wait(&a_empty[buf], ((k8 / NABUF) & 1) ^ 1);
+    for (int q = 0; q < nq; ++q) {
+      const int k8 = q >= nk8 ? q - nk8 : q;
+      const int buf = q % NABUF;
+      mbar_wait(&a_empty[buf], ((q / NABUF) & 1) ^ 1);
       float* ah = abuf + buf * Cfg::A_BUF_FLOATS;
       float* al = ah + 2 * ROWS * 4;
       // all global loads of a batch are issued before any is consumed (the loop is latency-, not bandwidth-bound)
