@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(256) stft_mag_kernel(const float* __restrict__
         int idx = t * hop + n - pad;
         if (idx < 0) idx = -idx;
         if (idx >= L) idx = 2 * (L - 1) - idx;
+        idx = max(0, min(idx, L - 1));   // (callers guarantee L > 384; never read out of bounds regardless)
         buf[0][n] = make_float2(w[idx] * win[n], 0.f);
       }
       __syncthreads();
