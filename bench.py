@@ -4,8 +4,10 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 32] [--secs 10] [--impl native|reference]
 
 A "step" is one pass of the hot path over one batch of synthetic utterances.  The default
-workload is BASELINE.json configs[1]: batch 32 x 10 s clips at 22.05 kHz on one B200 (fp32
-arithmetic -- stricter than the config's "fp16").  For N > 1 launch under torchrun: one rank per
+workload is BASELINE.json configs[1]: batch 32 x 10 s clips at 22.05 kHz on one B200, in the
+default arithmetic mode (--precision tf32x3: split-precision tensor-core convolutions, fp32-grade
+results -- stricter than the config's "fp16"; fp32 = CUDA cores only, tf32 = single pass).  The
+other modes are timed briefly in the same run and reported under "modes_audio_s_per_s".  For N > 1 launch under torchrun: one rank per
 GPU, every rank converts its own `batch` clips (weak scaling, no data-path collective; NCCL only
 broadcasts the checkpoint and, in the end-to-end leg, gathers the output waveforms on rank 0).
 
