@@ -240,6 +240,55 @@ class ToneColorConverter(OpenVoiceBaseClass):
                 out[i] = self.add_watermark(a, msg)
         return out  # type: ignore[return-value]
 
+    # receptive field of the whole path in spectrogram frames: enc_q +-32 (16 WN layers of k=5), flow forward and
+    # reverse +-32 each (4 couplings x 4 layers), generator +-13.3 (conv_pre 3, transposed convs, ResBlocks up to
+    # k=11 d=5) -> 110; 128 leaves margin (SURVEY.md section 5 "long-context": measured ~109)
+    HALO_FRAMES = 128
+
+    @torch.no_grad()
+    def convert_long(self, audio_src_path, src_se, tgt_se, output_path=None, tau=0.3, message="default",
+                     window_frames: int = 2048, noise=None, max_batch: int = 32):
+        """Row f4 (time-tiled execution): convert a clip of any length with bounded memory.  The spectrogram is
+        cut into windows of ``window_frames`` frames plus a halo of the path's receptive field on both sides; the
+        windows run as one ragged batch and only their interiors are kept, so the result equals ``convert`` on the
+        whole clip (same noise tensor: drawn once for the whole clip, or passed as ``noise`` [192, T])."""
+        hps = self.hps
+        hop, dev = hps.data.hop_length, self.device
+        wav = torch.from_numpy(_load_audio(audio_src_path, hps.data.sampling_rate)).to(dev)
+        L = wav.numel()
+        spec, _ = self.model.native.spectrogram(wav[None].contiguous(), torch.tensor([L], dtype=torch.int64, device=dev))
+        T = spec.shape[2]
+        C = hps.model.inter_channels
+        if noise is None:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
+            noise = torch.randn(C, T, device=dev, generator=gen)
+        noise = noise.to(dev, torch.float32).reshape(C, T)
+        H = self.HALO_FRAMES
+        starts = list(range(0, T, window_frames))
+        wins = [(max(0, s - H), min(T, s + window_frames + H), s, min(T, s + window_frames)) for s in starts]
+        Wmax = max(hi - lo for lo, hi, _, _ in wins)
+        out = torch.empty(T * hop, device=dev, dtype=torch.float32)
+        src = self._stack_se(src_se, 1)
+        tgt = self._stack_se(tgt_se, 1)
+        for i0 in range(0, len(wins), max_batch):
+            chunk = wins[i0: i0 + max_batch]
+            B = len(chunk)
+            sp = torch.zeros(B, spec.shape[1], Wmax, device=dev)
+            nz = torch.zeros(B, C, Wmax, device=dev)
+            for b, (lo, hi, _, _) in enumerate(chunk):
+                sp[b, :, : hi - lo] = spec[0, :, lo:hi]
+                nz[b, :, : hi - lo] = noise[:, lo:hi]
+            lens = torch.tensor([hi - lo for lo, hi, _, _ in chunk], dtype=torch.int64, device=dev)
+            o, _, _ = self.model.voice_conversion(sp, lens, src.expand(B, -1), tgt.expand(B, -1), tau=tau, noise=nz,
+                                                  ragged=True, latents=False)
+            for b, (lo, hi, s, e) in enumerate(chunk):
+                out[s * hop: e * hop] = o[b, 0, (s - lo) * hop: (e - lo) * hop]
+        audio = self.add_watermark(out.cpu().numpy(), message)
+        if output_path is None:
+            return audio
+        _write_audio(output_path, audio, hps.data.sampling_rate)
+
     def _stack_se(self, se, n):
         if isinstance(se, (list, tuple)):
             se = torch.cat([s.reshape(1, -1) for s in se], 0)

@@ -233,6 +233,31 @@ def test_full_size_batch_properties(tmp_path, synthetic_sd):
     assert not np.array_equal(d[0], a[0])            # a different seed draws different noise
 
 
+def test_time_tiled_long_clip_equals_whole_clip(tmp_path, synthetic_sd):
+    """convert_long (row f4: windows + receptive-field halo, one ragged batch) reproduces convert on the whole
+    clip: interiors do not see the window edges.  Both arithmetic modes; same explicit noise on both sides."""
+    from openvoice_b200.api import ToneColorConverter
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps(O.DEFAULT_HPARAMS))
+    rng = np.random.default_rng(11)
+    L = 22050 * 14 + 123
+    wav = (0.5 * (2 * rng.random(L, dtype=np.float32) - 1)).astype(np.float32)
+    T = L // 256
+    gen = torch.Generator().manual_seed(8)
+    src = 0.1 * torch.randn(1, 256, 1, generator=gen)
+    tgt = 0.1 * torch.randn(1, 256, 1, generator=gen)
+    noise = torch.randn(192, T, generator=gen)
+    for precision in ("fp32", "tf32x3"):
+        conv = ToneColorConverter(str(cfg), device="cuda:0", enable_watermark=False, precision=precision)
+        conv.model.load_state_dict(synthetic_sd)
+        whole = conv.convert(wav, src, tgt, tau=0.3, noise=noise[None])
+        tiled = conv.convert_long(wav, src, tgt, tau=0.3, noise=noise, window_frames=300)
+        assert tiled.shape == whole.shape == (256 * T,)
+        assert rel_err(tiled, whole) <= 2e-6, precision
+        short = conv.convert_long(wav[: 256 * 90], src, tgt, tau=0.0, window_frames=2048)     # single window
+        assert np.array_equal(short, conv.convert(wav[: 256 * 90], src, tgt, tau=0.0))
+
+
 def test_api_convert_matches_reference_golden(tmp_path, synthetic_sd):
     """ToneColorConverter.convert end to end (waveform -> spectrogram -> VC -> samples) against
     the real reference's convert() output."""
