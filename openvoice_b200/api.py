@@ -116,6 +116,7 @@ class NativeSynthesizer:
         unexpected = sorted(provided - expected)
         self.native.load_state_dict(state_dict)
         self.native.finalize()          # raises OvcError naming the first missing hot-path key
+        self._state_dict = state_dict   # kept (by reference) so that per-stream replicas can be built on demand
         if strict and (missing or unexpected):
             raise RuntimeError(f"missing keys {missing}, unexpected keys {unexpected}")
         return missing, unexpected
@@ -239,6 +240,64 @@ class ToneColorConverter(OpenVoiceBaseClass):
                 msg = messages[i] if messages is not None else "default"
                 out[i] = self.add_watermark(a, msg)
         return out  # type: ignore[return-value]
+
+    # ------------------------------------------------------------------ one utterance per stream
+    @torch.no_grad()
+    def convert_concurrent(self, audios: Sequence[AudioLike], src_se, tgt_se, tau: float = 0.3, streams: int = 4,
+                           messages: Optional[Sequence[str]] = None) -> List[np.ndarray]:
+        """Serve many SMALL independent requests: utterance i runs alone (batch 1, exactly ``convert``) on CUDA
+        stream ``i % streams``, each stream with its own converter replica (context + workspace), so the
+        latency-bound kernels of different requests overlap on the GPU -- north_star's "one utterance per stream".
+        For large batches ``convert_batch`` (one launch sequence for the whole batch) is the faster path."""
+        n = len(audios)
+        src = self._stack_se(src_se, n)
+        tgt = self._stack_se(tgt_se, n)
+        reps = self._replicas(max(1, min(streams, n)))
+        S, depth = len(reps), 2                       # requests in flight per stream (pinned staging slots)
+        out: List[Optional[np.ndarray]] = [None] * n
+        for w0 in range(0, n, S * depth):
+            wave = list(range(w0, min(n, w0 + S * depth)))
+            pending = []
+            for j, i in enumerate(wave):
+                conv, stream = reps[j % S]
+                with torch.cuda.stream(stream):
+                    pending.append(conv._enqueue_single(_load_audio(audios[i], self.hps.data.sampling_rate), src[i: i + 1],
+                                                        tgt[i: i + 1], tau, j // S))
+            for _, stream in reps:
+                stream.synchronize()
+            for i, (host, n_samples) in zip(wave, pending):
+                msg = messages[i] if messages is not None else "default"
+                out[i] = self.add_watermark(host[:n_samples].numpy().copy(), msg)
+        return out  # type: ignore[return-value]
+
+    def _replicas(self, count):
+        """[(converter, stream)]: replica 0 is this object; the others share its hparams and checkpoint."""
+        reps = self.__dict__.setdefault("_reps", [(self, torch.cuda.Stream(device=self.device))])
+        while len(reps) < count:
+            twin = ToneColorConverter.__new__(ToneColorConverter)
+            twin.hps, twin.device, twin.watermark_model, twin.version = self.hps, self.device, None, self.version
+            twin.model = NativeSynthesizer(self.hps, self.device, precision=self.model.precision)
+            twin.model.load_state_dict(self.model._state_dict)
+            reps.append((twin, torch.cuda.Stream(device=self.device)))
+        return reps[:count]
+
+    def _enqueue_single(self, wave, src, tgt, tau, slot):
+        """Asynchronous batch-1 conversion on the current stream, staging through pinned slot ``slot``;
+        returns (pinned host buffer, samples).  The caller synchronises the stream before reading / reusing it."""
+        hop = self.hps.data.hop_length
+        dev = self.device
+        L = len(wave)
+        if L // hop < 1 or L <= (self.hps.data.filter_length - hop) // 2:
+            raise ValueError("audio too short")
+        stage = self._pinned(f"cin{slot}", L)
+        stage.copy_(torch.from_numpy(wave))
+        wav = stage.to(dev, non_blocking=True).view(1, L)
+        wlen = torch.tensor([L], dtype=torch.int64, device=dev)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        o, _ = self.model.native.convert_waveform(wav, wlen, src, tgt, tau=float(tau), seed=seed)
+        host = self._pinned(f"cout{slot}", o.numel())
+        host.copy_(o.view(-1), non_blocking=True)
+        return host, (L // hop) * hop
 
     # receptive field of the whole path in spectrogram frames: enc_q +-32 (16 WN layers of k=5), flow forward and
     # reverse +-32 each (4 couplings x 4 layers), generator +-13.3 (conv_pre 3, transposed convs, ResBlocks up to

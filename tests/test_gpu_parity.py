@@ -233,6 +233,25 @@ def test_full_size_batch_properties(tmp_path, synthetic_sd):
     assert not np.array_equal(d[0], a[0])            # a different seed draws different noise
 
 
+def test_one_utterance_per_stream_equals_solo(tmp_path, synthetic_sd):
+    """convert_concurrent (replica + CUDA stream per in-flight request) returns exactly the solo conversions."""
+    from openvoice_b200.api import ToneColorConverter
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps(O.DEFAULT_HPARAMS))
+    conv = ToneColorConverter(str(cfg), device="cuda:0", enable_watermark=False)
+    conv.model.load_state_dict(synthetic_sd)
+    rng = np.random.default_rng(3)
+    wavs = [(0.5 * (2 * rng.random(n, dtype=np.float32) - 1)).astype(np.float32)
+            for n in (22050, 30000, 66150, 256 * 7 + 5, 44100, 22050 * 2, 51200, 9999, 70000, 12345, 33333)]
+    gen = torch.Generator().manual_seed(4)
+    src = 0.1 * torch.randn(1, 256, 1, generator=gen)
+    tgt = 0.1 * torch.randn(1, 256, 1, generator=gen)
+    res = conv.convert_concurrent(wavs, src, tgt, tau=0.0, streams=3)
+    assert len(res) == len(wavs)
+    for w, r in zip(wavs, res):
+        assert np.array_equal(r, conv.convert(w, src, tgt, tau=0.0))
+
+
 def test_time_tiled_long_clip_equals_whole_clip(tmp_path, synthetic_sd):
     """convert_long (row f4: windows + receptive-field halo, one ragged batch) reproduces convert on the whole
     clip: interiors do not see the window edges.  Both arithmetic modes; same explicit noise on both sides."""
