@@ -139,6 +139,32 @@ OVC_API int ovc_convert_waveform(ovc_ctx* ctx, const float* wav, const int64_t* 
  *   out   [N, gin]                                                                                          */
 OVC_API int ovc_reference_encoder(ovc_ctx* ctx, const float* spec, int N, int T, float* out, void* stream);
 
+/* ---- V1 base-speaker TTS front half: SynthesizerTrn.infer (openvoice/models.py:467-490), SURVEY.md section 8 row f3 ----
+ * Available when the checkpoint passed through ovc_load_tensor holds enc_p.* / dp.* / sdp.* / emb_g.* (a V1 base
+ * speaker, models.py:451-465); their hyper-parameters (n_vocab, heads, layers, window, filter sizes, n_speakers) are
+ * read off the tensor shapes.  infer() is split where the reference itself synchronises (y_lengths -> mask sizes,
+ * models.py:476-478):
+ *
+ *   ovc_tts_encode   x, m_p, logs_p = enc_p(tokens)                        models.py:468, 16-57; attentions.py:37-465
+ *                    g = emb_g(sid)                                          models.py:470
+ *                    logw = sdp(x, g, reverse) * ratio + dp(x, g) * (1 - ratio)   models.py:474-475, 60-180;
+ *                                                                             modules.py:84-130, 459-516; transforms.py
+ *                    w_ceil = ceil(exp(logw) * mask * length_scale); y_lengths = max(1, sum w_ceil)   models.py:477-479
+ *   ovc_tts_decode   attn = generate_path(w_ceil); m_p, logs_p expanded; z_p = m_p + noise * exp(logs_p) * noise_scale;
+ *                    z = flow(z_p, g, reverse); o = dec(z * y_mask, g)       models.py:480-490; commons.py:128-142
+ *
+ * tokens [B][T] int64 (padded), x_lengths [B] int64, sid [B] int64, noise_w [B][2][T] or NULL (Philox from `seed`);
+ * y_lengths [B] int64 out; w_ceil / logw [B][T] optional outs.  All device pointers.  ovc_tts_decode uses the state the
+ * last ovc_tts_encode left in the context: noise [B][inter][Ymax] or NULL (Philox), Ymax >= max(y_lengths) (a smaller
+ * value is the reference's max_len), ragged as in ovc_voice_conversion; o [B][Ymax*hop], z / z_p [B][inter][Ymax]
+ * optional.  ovc_tts_info: out8 = {has_tts, n_vocab, n_speakers, n_heads, n_layers, window, filter_channels, dp_filter}. */
+OVC_API int ovc_tts_info(const ovc_ctx* ctx, int32_t* out8);
+OVC_API int ovc_tts_encode(ovc_ctx* ctx, const int64_t* tokens, const int64_t* x_lengths, const int64_t* sid,
+                           const float* noise_w, uint64_t seed, float noise_scale_w, float length_scale, float sdp_ratio,
+                           int B, int T, int64_t* y_lengths, float* w_ceil, float* logw, void* stream);
+OVC_API int ovc_tts_decode(ovc_ctx* ctx, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int ragged,
+                           float* o, float* z, float* z_p, void* stream);
+
 /* Arithmetic of the generator's ResBlock convolutions (90 % of the FLOPs):
  *   0 (default)  fp32 FFMA2 on the CUDA cores
  *   1            split-precision 3xTF32 on the 5th-gen tensor cores (tcgen05 + TMEM): every product is

@@ -19,6 +19,7 @@ EXPORTS = (
     "ovc_finalize_weights", "ovc_workspace_floats", "ovc_voice_conversion", "ovc_last_launch_count",
     "ovc_profile_enable", "ovc_profile_read", "ovc_profile_detail", "ovc_debug_enable", "ovc_debug_fetch",
     "ovc_spectrogram", "ovc_convert_waveform", "ovc_set_precision", "ovc_reference_encoder",
+    "ovc_tts_info", "ovc_tts_encode", "ovc_tts_decode",
 )
 
 
@@ -79,6 +80,11 @@ def load_library(path: Optional[str] = None):
                                     C.c_void_p, C.c_void_p]
     lib.ovc_convert_waveform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ovc_tts_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    lib.ovc_tts_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float,
+                                   C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ovc_tts_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.ovc_abi_version() != ABI_VERSION:
         raise OvcError(f"ABI mismatch: library {lib.ovc_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
@@ -262,6 +268,53 @@ class NativeConverter:
                                             C.c_void_p(st.cuda_stream))
         _check(self.lib, rc, "ovc_reference_encoder")
         return out
+
+    # ---- V1 TTS front half (SynthesizerTrn.infer, openvoice/models.py:467-490) ----------------
+    def tts_info(self) -> dict:
+        out = (C.c_int32 * 8)()
+        _check(self.lib, self.lib.ovc_tts_info(self.handle, out), "ovc_tts_info")
+        keys = ("has_tts", "n_vocab", "n_speakers", "n_heads", "n_layers", "window", "filter_channels", "dp_filter")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def tts_encode(self, tokens, x_lengths, sid, noise_w=None, seed: int = 0, noise_scale_w: float = 1.0,
+                   length_scale: float = 1.0, sdp_ratio: float = 0.2, stream=None):
+        """tokens [B,T] i64 cuda, x_lengths [B] i64 cuda, sid [B] i64 cuda, noise_w [B,2,T] or None (Philox).
+        Returns (y_lengths [B] i64, w_ceil [B,T], logw [B,T]), all on the device; asynchronous on `stream`."""
+        import torch
+        for t in (tokens, x_lengths, sid):
+            assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()
+        B, T = tokens.shape
+        if noise_w is not None:
+            noise_w = noise_w.contiguous().float()
+            assert tuple(noise_w.shape) == (B, 2, T)
+        y_lengths = torch.empty(B, device=tokens.device, dtype=torch.int64)
+        w_ceil = torch.empty(B, T, device=tokens.device, dtype=torch.float32)
+        logw = torch.empty(B, T, device=tokens.device, dtype=torch.float32)
+        st = stream if stream is not None else torch.cuda.current_stream(tokens.device)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        rc = self.lib.ovc_tts_encode(self.handle, p(tokens), p(x_lengths), p(sid), p(noise_w), C.c_uint64(seed & (2 ** 64 - 1)),
+                                     C.c_float(noise_scale_w), C.c_float(length_scale), C.c_float(sdp_ratio), B, T,
+                                     p(y_lengths), p(w_ceil), p(logw), C.c_void_p(st.cuda_stream))
+        _check(self.lib, rc, "ovc_tts_encode")
+        return y_lengths, w_ceil, logw
+
+    def tts_decode(self, B: int, y_max: int, device, noise=None, seed: int = 0, noise_scale: float = 1.0,
+                   ragged: bool = False, latents: bool = False, stream=None):
+        """Second half of infer() for the last tts_encode.  Returns (o [B,1,hop*y_max], (z, z_p) or None)."""
+        import torch
+        C_ = self.hp.inter_channels
+        if noise is not None:
+            noise = noise.contiguous().float()
+            assert noise.is_cuda and tuple(noise.shape) == (B, C_, y_max)
+        o = torch.empty(B, 1, self.hp.hop_length * y_max, device=device, dtype=torch.float32)
+        lat = tuple(torch.empty(B, C_, y_max, device=device, dtype=torch.float32) for _ in range(2)) if latents else None
+        st = stream if stream is not None else torch.cuda.current_stream(device)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        rc = self.lib.ovc_tts_decode(self.handle, p(noise), C.c_uint64(seed & (2 ** 64 - 1)), C.c_float(noise_scale), B,
+                                     int(y_max), 1 if ragged else 0, p(o), p(lat[0]) if lat else None,
+                                     p(lat[1]) if lat else None, C.c_void_p(st.cuda_stream))
+        _check(self.lib, rc, "ovc_tts_decode")
+        return o, lat
 
     @property
     def last_launch_count(self) -> int:

@@ -20,7 +20,7 @@ from . import utils
 from ._native import NativeConverter
 from .mel_processing import spectrogram_torch
 from .ref_enc import ReferenceEncoder
-from .schema import hot_path_keys, ref_enc_keys
+from .schema import hot_path_keys, ref_enc_keys, tts_keys
 
 AudioLike = Union[str, np.ndarray]
 
@@ -86,16 +86,14 @@ class NativeSynthesizer:
         self.hps = hps
         self.zero_g = bool(getattr(hps.model, "zero_g", False))
         self.n_speakers = int(getattr(hps.data, "n_speakers", 0))
-        if self.n_speakers != 0:
-            raise ValueError("only the tone-colour converter (n_speakers == 0) is implemented; the V1 "
-                             "base-speaker TTS front half is out of this build's scope")
         index = dev.index if dev.index is not None else torch.cuda.current_device()
         self.native = NativeConverter(hps, index)
         self.precision = precision or os.environ.get("OVC_PRECISION", "tf32x3")
         self.native.set_precision(self.precision)
         self.spec_channels = hps.data.filter_length // 2 + 1
         self.ref_enc = ReferenceEncoder(self.native, self.spec_channels, int(getattr(hps.model, "gin_channels", 256)))
-        self._expected = hot_path_keys(hps) + ref_enc_keys()
+        # n_speakers == 0: converter (ReferenceEncoder); > 0: V1 base speaker (enc_p / dp / sdp / emb_g), models.py:451-465
+        self._expected = hot_path_keys(hps) + (ref_enc_keys() if self.n_speakers == 0 else tts_keys(hps))
 
     # nn.Module-ish surface used by callers of the reference
     def eval(self):
@@ -143,6 +141,53 @@ class NativeSynthesizer:
         y_mask = (torch.arange(T, device=self.device)[None, :] < y_lengths[:, None]).unsqueeze(1).to(torch.float32)
         return o, y_mask, lat
 
+    @torch.no_grad()
+    def infer(self, x, x_lengths, sid=None, noise_scale=1, length_scale=1, noise_scale_w=1.0, sdp_ratio=0.2,
+              max_len=None, noise_w=None, noise=None, ragged: bool = False, seed: Optional[int] = None,
+              latents: bool = True):
+        """(o, attn, y_mask, (z, z_p, None, None)) = SynthesizerTrn.infer (openvoice/models.py:467-490) for a V1
+        base-speaker checkpoint.  ``x`` [B,T] token ids, ``x_lengths`` [B], ``sid`` [B] speaker ids.
+        ``noise_w`` ([B,2,T]) / ``noise`` ([B,192,>=Ty]) replace the two random draws (models.py:173, 487); when None,
+        Philox normals are drawn in-kernel from ``seed``.  The expanded m_p / logs_p of the reference's return
+        tuple are not materialised (they only feed z_p).  One host sync, where the reference has one too
+        (y_lengths sizes every later tensor, models.py:476-478)."""
+        info = self.native.tts_info()
+        if not info["has_tts"]:
+            raise RuntimeError("this checkpoint has no enc_p / dp / sdp / emb_g: infer() needs a V1 base speaker")
+        x = x.to(torch.int64)
+        if int(x.min()) < 0 or int(x.max()) >= info["n_vocab"]:
+            raise ValueError(f"token ids must lie in [0, {info['n_vocab']})")
+        x = x.to(self.device).contiguous()
+        B, T = x.shape
+        x_lengths = x_lengths.to(self.device, torch.int64).contiguous()
+        if sid is None:
+            raise ValueError("sid is required (n_speakers > 0)")
+        sid = sid.to(torch.int64).reshape(-1)
+        if int(sid.min()) < 0 or int(sid.max()) >= info["n_speakers"]:
+            raise ValueError(f"speaker ids must lie in [0, {info['n_speakers']})")
+        sid = sid.to(self.device).contiguous()
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if noise_w is not None:
+            noise_w = noise_w.to(self.device, torch.float32)
+        y_lengths, w_ceil, _ = self.native.tts_encode(x, x_lengths, sid, noise_w=noise_w, seed=seed,
+                                                      noise_scale_w=float(noise_scale_w), length_scale=float(length_scale),
+                                                      sdp_ratio=float(sdp_ratio))
+        Ty = int(y_lengths.max().item())                       # the sync
+        if max_len is not None:
+            Ty = min(Ty, int(max_len))
+        if noise is not None:
+            noise = noise.to(self.device, torch.float32)[:, :, :Ty].contiguous()
+        o, lat = self.native.tts_decode(B, Ty, self.device, noise=noise, seed=seed + 1, noise_scale=float(noise_scale),
+                                        ragged=ragged, latents=latents)
+        ar = torch.arange(Ty, device=self.device)
+        y_mask = (ar[None, :] < y_lengths[:, None]).unsqueeze(1).to(torch.float32)
+        cum = torch.cumsum(w_ceil, 1)                          # commons.generate_path (commons.py:128-142)
+        path = (ar[None, :, None] < cum[:, None, :]) & (ar[None, :, None] >= (cum - w_ceil)[:, None, :])
+        attn = (path.to(torch.float32) * y_mask.transpose(1, 2)).unsqueeze(1)      # [B,1,Ty,T]
+        z, z_p = lat if lat else (None, None)
+        return o, attn, y_mask, (z, z_p, None, None)
+
     def _expand_se(self, se, B):
         se = se.to(self.device, torch.float32).reshape(se.shape[0], -1)
         if se.shape[0] == 1 and B > 1:
@@ -168,6 +213,86 @@ class OpenVoiceBaseClass(object):
         a, b = self.model.load_state_dict(checkpoint_dict["model"], strict=False)
         print("Loaded checkpoint '{}'".format(ckpt_path))
         print("missing/unexpected keys:", a, b)
+
+
+class BaseSpeakerTTS(OpenVoiceBaseClass):
+    """openvoice/api.py:42-98: the V1 base speaker.  The acoustic model (``SynthesizerTrn.infer``) runs on the
+    CUDA library; the text front end (sentence splitting, cleaners, G2P: openvoice/text/*, utils.split_sentence)
+    is host-side string processing outside this build's scope, so it is pluggable:
+    ``text_frontend(text, language_mark) -> list of token-id lists`` (one per sentence, blanks already
+    interspersed).  When the reference package is importable its own front end is used."""
+
+    language_marks = {"english": "EN", "chinese": "ZH"}
+
+    def __init__(self, *args, text_frontend=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.text_frontend = text_frontend
+
+    @staticmethod
+    def intersperse(lst, item):
+        """commons.intersperse (openvoice/commons.py:22-25): [a, b] -> [item, a, item, b, item]."""
+        out = [item] * (len(lst) * 2 + 1)
+        out[1::2] = lst
+        return out
+
+    @staticmethod
+    def audio_numpy_concat(segment_data_list, sr, speed=1.0):
+        """openvoice/api.py:56-63: sentences joined with 50 ms / speed of silence after each."""
+        gap = np.zeros(int((sr * 0.05) / speed), dtype=np.float32)
+        parts = []
+        for seg in segment_data_list:
+            parts += [np.asarray(seg, dtype=np.float32).reshape(-1), gap]
+        return np.concatenate(parts) if parts else np.zeros(0, np.float32)
+
+    def _reference_frontend(self, text, mark):
+        try:
+            import re
+            from openvoice import utils as ref_utils          # type: ignore
+            from openvoice.text import text_to_sequence      # type: ignore
+        except ImportError as e:
+            raise RuntimeError("no text front end: pass text_frontend=... to BaseSpeakerTTS, call tts_from_ids(), or "
+                               "install the reference package for its cleaners") from e
+        seqs = []
+        for t in ref_utils.split_sentence(text, language_str=mark):              # api.py:66-71
+            t = re.sub(r"([a-z])([A-Z])", r"\1 \2", t)                           # api.py:81
+            ids = text_to_sequence(f"[{mark}]{t}[{mark}]", self.hps.symbols, self.hps.data.text_cleaners)
+            if getattr(self.hps.data, "add_blank", False):
+                ids = self.intersperse(ids, 0)                                   # api.py:50-52
+            seqs.append(ids)
+        return seqs
+
+    @torch.no_grad()
+    def tts_from_ids(self, sequences, speaker, speed=1.0, noise_scale=0.667, noise_scale_w=0.6, sdp_ratio=0.2,
+                     seed: Optional[int] = None) -> List[np.ndarray]:
+        """All sentences in ONE batched infer() (the reference loops over them at batch 1, api.py:79-91); every
+        sentence gets what its own batch-1 call would give (ragged decode)."""
+        speaker_id = self.hps.speakers[speaker] if isinstance(speaker, str) else int(speaker)
+        n = len(sequences)
+        T = max(len(q) for q in sequences)
+        x = torch.zeros(n, T, dtype=torch.int64)
+        for i, q in enumerate(sequences):
+            x[i, :len(q)] = torch.as_tensor(q, dtype=torch.int64)
+        lens = torch.tensor([len(q) for q in sequences], dtype=torch.int64)
+        sid = torch.full((n,), speaker_id, dtype=torch.int64)
+        o, _, y_mask, _ = self.model.infer(x, lens, sid=sid, noise_scale=noise_scale, noise_scale_w=noise_scale_w,
+                                           length_scale=1.0 / speed, sdp_ratio=sdp_ratio, ragged=True, seed=seed,
+                                           latents=False)
+        frames = y_mask[:, 0].sum(1).long().cpu()
+        o = o[:, 0].float().cpu().numpy()
+        hop = self.hps.data.hop_length
+        return [o[i, : int(frames[i]) * hop].copy() for i in range(n)]
+
+    def tts(self, text, output_path, speaker, language="English", speed=1.0):
+        """openvoice/api.py:73-98."""
+        mark = self.language_marks.get(language.lower(), None)
+        assert mark is not None, f"language {language} is not supported"
+        frontend = self.text_frontend or self._reference_frontend
+        sequences = frontend(text, mark)
+        audio_list = self.tts_from_ids(sequences, speaker, speed=speed)
+        audio = self.audio_numpy_concat(audio_list, sr=self.hps.data.sampling_rate, speed=speed)
+        if output_path is None:
+            return audio
+        _write_audio(output_path, audio, self.hps.data.sampling_rate)
 
 
 class ToneColorConverter(OpenVoiceBaseClass):

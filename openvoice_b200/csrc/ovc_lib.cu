@@ -16,6 +16,7 @@
 #include "../../include/ovc.h"
 #include "ovc_small.cuh"
 #include "ovc_tcconv.cuh"
+#include "ovc_tts.cuh"
 #include "ovc_refenc.cuh"
 #include "ovc_variants.h"
 
@@ -94,6 +95,26 @@ struct WNLayers {
   std::vector<TcLayer> tc_in, tc_rs;   // tensor-core twins (channels-last)
 };
 
+// V1 TTS front half (TextEncoder / DurationPredictor / StochasticDurationPredictor, models.py:16-180): dense convs
+// as tensor-core layers, small fp32 parameters as offsets into the fp32 arena.  Hyper-parameters are read off the
+// checkpoint shapes (the reference takes them from config.json: api.py:26-31, models.py:451-465).
+struct DdsLayers {            // DDSConv, modules.py:84-113
+  size_t sep_w[3] = {0}, sep_b[3] = {0}, n1g[3] = {0}, n1b[3] = {0}, n2g[3] = {0}, n2b[3] = {0};
+  TcLayer c1x1[3];
+};
+struct TtsLayers {
+  bool ready = false;
+  int n_vocab = 0, n_speakers = 0, H = 0, C = 0, Fc = 0, heads = 0, n_layers = 0, window = 0, D = 0;
+  size_t emb = 0, emb_g = 0;
+  std::vector<TcLayer> qkv, o, ffn1, ffn2;
+  std::vector<size_t> relk, relv, ln1g, ln1b, ln2g, ln2b;
+  TcLayer proj, dp_c1, dp_c2, sdp_pre, sdp_proj;
+  size_t dp_n1g = 0, dp_n1b = 0, dp_n2g = 0, dp_n2b = 0, dp_pw = 0, dp_pb = 0, dp_cw = 0, dp_cb = 0, sdp_cw = 0, sdp_cb = 0,
+         ea = 0;               // ea: {m[0], logs[0]} of sdp.flows.0
+  DdsLayers dds[4];            // 0: sdp.convs, j = 1..3: sdp.flows.{2j+1}.convs (flows.1 is never run in reverse, models.py:172)
+  size_t cf_pre_w[4] = {0}, cf_pre_b[4] = {0}, cf_pw[4] = {0}, cf_pb[4] = {0};
+};
+
 struct DebugBuf {
   float* d = nullptr;
   int64_t shape[4] = {0, 0, 0, 0};
@@ -150,6 +171,12 @@ struct ovc_ctx {
   // workspace
   float* d_ws = nullptr;
   size_t ws_floats = 0;
+
+  // TTS front half: layers, text-side workspace, and what ovc_tts_encode leaves for ovc_tts_decode
+  TtsLayers tts;
+  float* d_tts = nullptr;
+  size_t tts_floats = 0;
+  int tts_B = 0, tts_T = 0;
 
   // profiling
   bool prof = false;
@@ -277,7 +304,9 @@ static int validate_hparams(const ovc_hparams* hp) {
 }
 
 static bool key_is_hot(const std::string& k) {
-  return k.rfind("enc_q.", 0) == 0 || k.rfind("flow.", 0) == 0 || k.rfind("dec.", 0) == 0 || k.rfind("ref_enc.", 0) == 0;
+  if (k.rfind("sdp.post_", 0) == 0) return false;   // training-only half of the SDP (models.py:118-125)
+  return k.rfind("enc_q.", 0) == 0 || k.rfind("flow.", 0) == 0 || k.rfind("dec.", 0) == 0 || k.rfind("ref_enc.", 0) == 0 ||
+         k.rfind("enc_p.", 0) == 0 || k.rfind("dp.", 0) == 0 || k.rfind("sdp.", 0) == 0 || k.rfind("emb_g.", 0) == 0;
 }
 
 static int pack_wn(ovc_ctx* c, const std::string& prefix, int n_layers, WNLayers* out, std::string* missing) {
@@ -360,6 +389,131 @@ static int pack_wn_tc(ovc_ctx* c, const std::string& prefix, int n_layers, WNLay
         [&](int p) { return rb->data[p]; }));
   }
   return 0;
+}
+
+// ---- V1 TTS front half: TextEncoder (models.py:16-57, attentions.py:37-121), DurationPredictor (models.py:60-100),
+// StochasticDurationPredictor reverse path (models.py:102-143), emb_g (models.py:465).  Every hyper-parameter is read
+// off the tensor shapes.
+static int pack_tts(ovc_ctx* c) {
+  TtsLayers& L = c->tts;
+  const ovc_hparams& hp = c->hp;
+  std::string err;
+  auto get = [&](const std::string& k, std::initializer_list<int64_t> shape) -> const HostTensor* {
+    const HostTensor* t = find(c, k);
+    if (!t) { if (err.empty()) err = "checkpoint tensor '" + k + "' is missing"; return nullptr; }
+    if (shape.size()) {
+      bool ok = t->shape.size() == shape.size();
+      size_t i = 0;
+      for (int64_t d : shape) { if (ok && d >= 0 && t->shape[i] != d) ok = false; ++i; }
+      if (!ok) { if (err.empty()) err = "checkpoint tensor '" + k + "' has the wrong shape"; return nullptr; }
+    }
+    return t;
+  };
+  auto put = [&](const HostTensor* t) -> size_t {
+    if (!t) return 0;
+    const size_t o = round_up(c->h_w.size(), 64);
+    c->h_w.resize(o + t->data.size());
+    std::copy(t->data.begin(), t->data.end(), c->h_w.begin() + o);
+    return o;
+  };
+  // dense conv [Cout][Cin][K] -> tensor-core layer
+  auto dense = [&](const std::string& prefix, int cout, int cin, int k) -> TcLayer {
+    const HostTensor* w = get(prefix + ".weight", {cout, cin, k});
+    const HostTensor* b = get(prefix + ".bias", {cout});
+    if (!w || !b) return TcLayer();
+    return pack_tc(c, cout, cin, k, 1, [&](int n, int ci, int tap) { return w->data[((size_t)n * cin + ci) * k + tap]; },
+                   [&](int n) { return b->data[n]; });
+  };
+
+  const HostTensor* emb = get("enc_p.emb.weight", {-1, -1});
+  if (!emb) return fail(OVC_ERR_MISSING, "%s", err.c_str());
+  L.n_vocab = (int)emb->shape[0];
+  L.H = (int)emb->shape[1];
+  L.C = hp.inter_channels;
+  const int H = L.H, G = hp.gin_channels;
+  if (H != hp.hidden_channels) return fail(OVC_ERR_INVALID, "enc_p.emb.weight has %d channels, hidden_channels is %d", H, hp.hidden_channels);
+  const HostTensor* rk0 = get("enc_p.encoder.attn_layers.0.emb_rel_k", {1, -1, -1});
+  const HostTensor* f10 = get("enc_p.encoder.ffn_layers.0.conv_1.weight", {-1, H, -1});
+  const HostTensor* dp1 = get("dp.conv_1.weight", {-1, H, 3});
+  const HostTensor* eg = get("emb_g.weight", {-1, G});
+  if (!rk0 || !f10 || !dp1 || !eg) return fail(OVC_ERR_MISSING, "%s", err.c_str());
+  const int dk = (int)rk0->shape[2];
+  L.window = ((int)rk0->shape[1] - 1) / 2;
+  L.heads = dk > 0 ? H / dk : 0;
+  L.Fc = (int)f10->shape[0];
+  const int fk = (int)f10->shape[2];
+  L.D = (int)dp1->shape[0];
+  L.n_speakers = (int)eg->shape[0];
+  if (L.heads < 1 || L.heads * dk != H || fk % 2 == 0 || H % 32 || L.Fc % 32 || L.D % 32 || (2 * L.C) % 32)
+    return fail(OVC_ERR_INVALID, "unsupported TTS geometry (H %d, heads %d, filter %d, ffn kernel %d, dp filter %d)", H, L.heads,
+                L.Fc, fk, L.D);
+  while (find(c, "enc_p.encoder.attn_layers." + std::to_string(L.n_layers) + ".conv_q.weight")) ++L.n_layers;
+  if (L.n_layers < 1) return fail(OVC_ERR_MISSING, "enc_p.encoder has no attention layers");
+
+  L.emb = put(emb);
+  L.emb_g = put(eg);
+  for (int i = 0; i < L.n_layers; ++i) {
+    const std::string a = "enc_p.encoder.attn_layers." + std::to_string(i);
+    const HostTensor *wq = get(a + ".conv_q.weight", {H, H, 1}), *wk = get(a + ".conv_k.weight", {H, H, 1}),
+                     *wv = get(a + ".conv_v.weight", {H, H, 1}), *bq = get(a + ".conv_q.bias", {H}),
+                     *bk = get(a + ".conv_k.bias", {H}), *bv = get(a + ".conv_v.bias", {H});
+    if (!wq || !wk || !wv || !bq || !bk || !bv) break;
+    const HostTensor* ws3[3] = {wq, wk, wv};
+    const HostTensor* bs3[3] = {bq, bk, bv};
+    // q | k | v stacked into one 1x1 conv H -> 3H (attentions.py:263-265)
+    L.qkv.push_back(pack_tc(c, 3 * H, H, 1, 1, [&](int n, int ci, int) { return ws3[n / H]->data[(size_t)(n % H) * H + ci]; },
+                            [&](int n) { return bs3[n / H]->data[n % H]; }));
+    L.o.push_back(dense(a + ".conv_o", H, H, 1));
+    L.relk.push_back(put(get(a + ".emb_rel_k", {1, 2 * L.window + 1, dk})));
+    L.relv.push_back(put(get(a + ".emb_rel_v", {1, 2 * L.window + 1, dk})));
+    const std::string e = "enc_p.encoder.";
+    L.ln1g.push_back(put(get(e + "norm_layers_1." + std::to_string(i) + ".gamma", {H})));
+    L.ln1b.push_back(put(get(e + "norm_layers_1." + std::to_string(i) + ".beta", {H})));
+    L.ln2g.push_back(put(get(e + "norm_layers_2." + std::to_string(i) + ".gamma", {H})));
+    L.ln2b.push_back(put(get(e + "norm_layers_2." + std::to_string(i) + ".beta", {H})));
+    L.ffn1.push_back(dense(e + "ffn_layers." + std::to_string(i) + ".conv_1", L.Fc, H, fk));
+    L.ffn2.push_back(dense(e + "ffn_layers." + std::to_string(i) + ".conv_2", H, L.Fc, fk));
+  }
+  L.proj = dense("enc_p.proj", 2 * L.C, H, 1);
+  // DurationPredictor
+  L.dp_c1 = dense("dp.conv_1", L.D, H, 3);
+  L.dp_c2 = dense("dp.conv_2", L.D, L.D, 3);
+  L.dp_n1g = put(get("dp.norm_1.gamma", {L.D})); L.dp_n1b = put(get("dp.norm_1.beta", {L.D}));
+  L.dp_n2g = put(get("dp.norm_2.gamma", {L.D})); L.dp_n2b = put(get("dp.norm_2.beta", {L.D}));
+  L.dp_pw = put(get("dp.proj.weight", {1, L.D, 1})); L.dp_pb = put(get("dp.proj.bias", {1}));
+  L.dp_cw = put(get("dp.cond.weight", {H, G, 1})); L.dp_cb = put(get("dp.cond.bias", {H}));
+  // StochasticDurationPredictor, reverse path
+  L.sdp_pre = dense("sdp.pre", H, H, 1);
+  L.sdp_proj = dense("sdp.proj", H, H, 1);
+  L.sdp_cw = put(get("sdp.cond.weight", {H, G, 1})); L.sdp_cb = put(get("sdp.cond.bias", {H}));
+  {
+    const HostTensor* m = get("sdp.flows.0.m", {2, 1});
+    const HostTensor* lg = get("sdp.flows.0.logs", {2, 1});
+    if (m && lg) {
+      HostTensor t; t.shape = {2}; t.data = {m->data[0], lg->data[0]};   // logw is channel 0 (models.py:178-179)
+      L.ea = put(&t);
+    }
+  }
+  for (int j = 0; j < 4; ++j) {
+    const std::string p = j == 0 ? std::string("sdp.convs") : "sdp.flows." + std::to_string(2 * j + 1) + ".convs";
+    DdsLayers& d = L.dds[j];
+    for (int i = 0; i < 3; ++i) {
+      const std::string n = std::to_string(i);
+      d.sep_w[i] = put(get(p + ".convs_sep." + n + ".weight", {H, 1, 3}));
+      d.sep_b[i] = put(get(p + ".convs_sep." + n + ".bias", {H}));
+      d.n1g[i] = put(get(p + ".norms_1." + n + ".gamma", {H})); d.n1b[i] = put(get(p + ".norms_1." + n + ".beta", {H}));
+      d.n2g[i] = put(get(p + ".norms_2." + n + ".gamma", {H})); d.n2b[i] = put(get(p + ".norms_2." + n + ".beta", {H}));
+      d.c1x1[i] = dense(p + ".convs_1x1." + n, H, H, 1);
+    }
+    if (j > 0) {
+      const std::string f = "sdp.flows." + std::to_string(2 * j + 1);
+      L.cf_pre_w[j] = put(get(f + ".pre.weight", {H, 1, 1})); L.cf_pre_b[j] = put(get(f + ".pre.bias", {H}));
+      L.cf_pw[j] = put(get(f + ".proj.weight", {ovc_tts::NP, H, 1})); L.cf_pb[j] = put(get(f + ".proj.bias", {ovc_tts::NP}));
+    }
+  }
+  if (!err.empty()) return fail(OVC_ERR_MISSING, "%s", err.c_str());
+  L.ready = true;
+  return OVC_OK;
 }
 
 static int finalize(ovc_ctx* c) {
@@ -573,6 +727,12 @@ static int finalize(ovc_ctx* c) {
     c->re_wih = put(wih->data); c->re_whh = put(whh->data); c->re_bih = put(bih->data); c->re_bhh = put(bhh->data);
     c->re_pw = put(rpw->data); c->re_pb = put(rpb->data); c->re_lng = put(lng->data); c->re_lnb = put(lnb->data);
     c->has_refenc = true;
+  }
+  // ---- V1 TTS front half (optional: base-speaker checkpoints only, models.py:451-465)
+  c->tts = TtsLayers();
+  if (find(c, "enc_p.emb.weight")) {
+    const int rc = pack_tts(c);
+    if (rc != OVC_OK) return rc;
   }
 #undef NEED
 #undef WEFF
@@ -916,74 +1076,22 @@ static int ensure_ws(ovc_ctx* c, const WsLayout& W, int B, int Tmax, cudaStream_
   return OVC_OK;
 }
 
-static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long* lens, const float* g_src, const float* g_tgt,
-                  const float* noise, uint64_t seed, float tau, int B, int Tmax, int ragged, float* o_hat,
-                  float* z_out, float* zp_out, float* zh_out, cudaStream_t st) {
-  const WsLayout W = ws_layout(c, B, Tmax);
-  TRY(ensure_ws(c, W, B, Tmax, st));
-  float* ws = c->d_ws;
-  Run r{c, st, B, Tmax, W.P, lens, ragged ? lens : nullptr, (double)B * Tmax};
-  c->launches = 0;
-  const int P = W.P;
+// z (workspace, [B][192][P]) -> a caller tensor [B][192][Tmax], zero past each length
+static int copy_latent_out(Run& r, const WsLayout& W, float* ws, float* dst) {
+  if (!dst) return OVC_OK;
+  dim3 grid((r.Tmax + 255) / 256, 192, r.B);
+  copy_latent_kernel<<<grid, 256, 0, r.st>>>(ws + W.z, W.P, dst, r.Tmax, 192, r.lens);
+  CK(cudaGetLastError());
+  r.c->launches++;
+  return OVC_OK;
+}
+
+// HiFi-GAN generator on the latent in ws.z (models.py:272-291): shared by voice_conversion and the TTS decode
+static int run_dec(Run& r, const WsLayout& W, float* ws, const float* cond, const long long* lens, float* o_hat) {
+  ovc_ctx* c = r.c;
+  cudaStream_t st = r.st;
+  const int B = r.B, Tmax = r.Tmax, P = W.P;
   const long long bs192 = 192LL * P;
-
-  // ---- every speaker-conditioning 1x1 conv in one launch
-  {
-    CondArgs a;
-    a.w = c->d_w + c->cond_w_off; a.bias = c->d_w + c->cond_b_off;
-    a.w_row = c->d_cond_wrow; a.sel = c->d_cond_sel;
-    a.g_src = g_src; a.g_tgt = g_tgt; a.out = ws + W.cond;
-    a.rows_out = c->cond_rows_out; a.gin = c->hp.gin_channels;
-    dim3 grid((c->cond_rows_out + 7) / 8, B);
-    cond_kernel<<<grid, 256, 0, st>>>(a);
-    CK(cudaGetLastError());
-    c->launches++;
-  }
-  const float* cond = ws + W.cond;
-  TRY(tap(r, "cond", cond, 1, c->cond_rows_out, c->cond_rows_out));
-
-  // ---- posterior encoder (models.py:212-221)
-  {
-    ConvArgs a{};
-    a.x = spec; a.x_bs = (long long)c->hp.spec_channels * spec_pitch; a.x_pitch = spec_pitch;
-    a.bias = c->d_w + c->enc_pre.b_off; a.bias_bs = 0;
-    a.y = ws + W.x; a.y_bs = bs192; a.y_pitch = P;
-    a.lens_in = lens; a.lens_out = lens; a.mul_in = 1; a.mul_out = 1;
-    a.slope = 1.f; a.scale = 1.f;
-    const bool aligned = (spec_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(spec) & 15) == 0);
-    TRY(launch(r, aligned ? c->enc_pre16 : c->enc_pre, a, Tmax));
-    TRY(tap(r, "enc.pre", ws + W.x, 192, Tmax, P));
-    if (c->precision >= 1) {
-      TRY(run_wn_tc(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, ws + W.bufA, ws + W.bufB, cond + c->cond_off_enc_tc,
-                    c->cond_rows_out));
-    } else {
-      TRY(run_wn(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, cond + c->cond_off_enc, c->cond_rows_out));
-    }
-    TRY(tap(r, "enc.wn", ws + W.skip, 192, Tmax, P));
-    ConvArgs p{};
-    p.x = ws + W.skip; p.x_bs = bs192; p.x_pitch = P;
-    p.bias = c->d_w + c->enc_proj.b_off; p.bias_bs = 0;
-    p.y = ws + W.z; p.y_bs = bs192; p.y_pitch = P;
-    p.r = noise; p.r_bs = 192LL * Tmax; p.r_pitch = Tmax;
-    p.lens_in = lens; p.lens_out = lens; p.mul_in = 1; p.mul_out = 1;
-    p.slope = 1.f; p.tau = tau; p.seed = seed;
-    TRY(launch(r, c->enc_proj, p, Tmax));
-  }
-  auto copy_latent = [&](float* dst) -> int {
-    if (!dst) return OVC_OK;
-    dim3 grid((Tmax + 255) / 256, 192, B);
-    copy_latent_kernel<<<grid, 256, 0, st>>>(ws + W.z, P, dst, Tmax, 192, lens);
-    CK(cudaGetLastError());
-    c->launches++;
-    return OVC_OK;
-  };
-  TRY(copy_latent(z_out));
-  // ---- flow forward with g_src, reverse with g_tgt (models.py:496-497)
-  TRY(run_flow(r, W, ws, false, cond));
-  TRY(copy_latent(zp_out));
-  TRY(run_flow(r, W, ws, true, cond));
-  TRY(copy_latent(zh_out));
-
   // ---- generator (models.py:272-291).  Lengths: frames * cumulative upsampling.
   {
     ConvArgs a{};
@@ -1108,6 +1216,267 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
   return OVC_OK;
 }
 
+static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long* lens, const float* g_src, const float* g_tgt,
+                  const float* noise, uint64_t seed, float tau, int B, int Tmax, int ragged, float* o_hat,
+                  float* z_out, float* zp_out, float* zh_out, cudaStream_t st) {
+  const WsLayout W = ws_layout(c, B, Tmax);
+  TRY(ensure_ws(c, W, B, Tmax, st));
+  float* ws = c->d_ws;
+  Run r{c, st, B, Tmax, W.P, lens, ragged ? lens : nullptr, (double)B * Tmax};
+  c->launches = 0;
+  const int P = W.P;
+  const long long bs192 = 192LL * P;
+
+  // ---- every speaker-conditioning 1x1 conv in one launch
+  {
+    CondArgs a;
+    a.w = c->d_w + c->cond_w_off; a.bias = c->d_w + c->cond_b_off;
+    a.w_row = c->d_cond_wrow; a.sel = c->d_cond_sel;
+    a.g_src = g_src; a.g_tgt = g_tgt; a.out = ws + W.cond;
+    a.rows_out = c->cond_rows_out; a.gin = c->hp.gin_channels;
+    dim3 grid((c->cond_rows_out + 7) / 8, B);
+    cond_kernel<<<grid, 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  const float* cond = ws + W.cond;
+  TRY(tap(r, "cond", cond, 1, c->cond_rows_out, c->cond_rows_out));
+
+  // ---- posterior encoder (models.py:212-221)
+  {
+    ConvArgs a{};
+    a.x = spec; a.x_bs = (long long)c->hp.spec_channels * spec_pitch; a.x_pitch = spec_pitch;
+    a.bias = c->d_w + c->enc_pre.b_off; a.bias_bs = 0;
+    a.y = ws + W.x; a.y_bs = bs192; a.y_pitch = P;
+    a.lens_in = lens; a.lens_out = lens; a.mul_in = 1; a.mul_out = 1;
+    a.slope = 1.f; a.scale = 1.f;
+    const bool aligned = (spec_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(spec) & 15) == 0);
+    TRY(launch(r, aligned ? c->enc_pre16 : c->enc_pre, a, Tmax));
+    TRY(tap(r, "enc.pre", ws + W.x, 192, Tmax, P));
+    if (c->precision >= 1) {
+      TRY(run_wn_tc(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, ws + W.bufA, ws + W.bufB, cond + c->cond_off_enc_tc,
+                    c->cond_rows_out));
+    } else {
+      TRY(run_wn(r, c->enc_wn, ws + W.x, ws + W.skip, ws + W.acts, cond + c->cond_off_enc, c->cond_rows_out));
+    }
+    TRY(tap(r, "enc.wn", ws + W.skip, 192, Tmax, P));
+    ConvArgs p{};
+    p.x = ws + W.skip; p.x_bs = bs192; p.x_pitch = P;
+    p.bias = c->d_w + c->enc_proj.b_off; p.bias_bs = 0;
+    p.y = ws + W.z; p.y_bs = bs192; p.y_pitch = P;
+    p.r = noise; p.r_bs = 192LL * Tmax; p.r_pitch = Tmax;
+    p.lens_in = lens; p.lens_out = lens; p.mul_in = 1; p.mul_out = 1;
+    p.slope = 1.f; p.tau = tau; p.seed = seed;
+    TRY(launch(r, c->enc_proj, p, Tmax));
+  }
+  auto copy_latent = [&](float* dst) -> int { return copy_latent_out(r, W, ws, dst); };
+  TRY(copy_latent(z_out));
+  // ---- flow forward with g_src, reverse with g_tgt (models.py:496-497)
+  TRY(run_flow(r, W, ws, false, cond));
+  TRY(copy_latent(zp_out));
+  TRY(run_flow(r, W, ws, true, cond));
+  TRY(copy_latent(zh_out));
+
+  return run_dec(r, W, ws, cond, lens, o_hat);
+}
+
+// ---------------------------------------------------------------------------------------------
+// V1 TTS front half (SynthesizerTrn.infer, models.py:467-490)
+// ---------------------------------------------------------------------------------------------
+struct TtsWs {   // float offsets into c->d_tts; rows R = B * T, channels-last
+  size_t g, cv, X, QKV, S, A, Y, F, STATS, DX, D1, D2, SX, XC, HH, Y1, Y2, z0, z1, lws, lwd, logw, wceil, cum, ylen, total;
+};
+static TtsWs tts_ws_layout(const ovc_ctx* c, int B, int T) {
+  const TtsLayers& L = c->tts;
+  const size_t R = (size_t)B * T;
+  TtsWs W;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = round_up(o + n, 64); return r; };
+  W.g = take((size_t)B * c->hp.gin_channels);
+  W.cv = take((size_t)B * L.H);
+  W.X = take(R * L.H); W.QKV = take(R * 3 * L.H); W.S = take((size_t)B * L.heads * T * T);
+  W.A = take(R * L.H); W.Y = take(R * L.H); W.F = take(R * L.Fc); W.STATS = take(R * 2 * L.C);
+  W.DX = take(R * L.H); W.D1 = take(R * L.D); W.D2 = take(R * L.D);
+  W.SX = take(R * L.H); W.XC = take(R * L.H); W.HH = take(R * L.H); W.Y1 = take(R * L.H); W.Y2 = take(R * L.H);
+  W.z0 = take(R); W.z1 = take(R); W.lws = take(R); W.lwd = take(R); W.logw = take(R); W.wceil = take(R);
+  W.cum = take(R);                 // int32
+  W.ylen = take((size_t)2 * B + 4);   // int64
+  W.total = o;
+  return W;
+}
+
+static int tts_tap(Run& r, const char* name, const float* src, int C) {   // channels-last [B][T][C] -> shape (B, T, C, C)
+  return tap(r, name, src, r.Tmax, C, C);
+}
+
+// text -> durations.  Leaves m_p / logs_p (STATS), cumulative durations, y_lengths and g in c->d_tts.
+static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* lens, const long long* sid,
+                          const float* noise_w, uint64_t seed, float noise_scale_w, float length_scale, float sdp_ratio, int B,
+                          int T, long long* y_lengths, float* w_ceil_out, float* logw_out, cudaStream_t st) {
+  const TtsLayers& L = c->tts;
+  const TtsWs W = tts_ws_layout(c, B, T);
+  if (W.total > c->tts_floats) {
+    CK(cudaStreamSynchronize(st));
+    if (c->d_tts) CK(cudaFree(c->d_tts));
+    c->d_tts = nullptr; c->tts_floats = 0;
+    if (cudaMalloc(&c->d_tts, W.total * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(OVC_ERR_NOMEM, "TTS workspace of %.2f GB for B=%d T=%d does not fit", W.total * 4e-9, B, T);
+    }
+    c->tts_floats = W.total;
+  }
+  c->tts_B = 0;
+  float* ws = c->d_tts;
+  const float* P = c->d_w;          // fp32 parameter arena
+  Run r{c, st, B, T, T, lens, lens, (double)B * T};
+  c->launches = 0;
+  const int H = L.H, G = c->hp.gin_channels;
+  const dim3 gE((T * H + 255) / 256, B), gRow((T + 63) / 64, B);
+  TcExtra tx; tx.use_lens_frames = true;
+  auto dense = [&](const TcLayer& lay, const float* x, float* y, float slope) -> int {
+    return launch_tc(r, lay, x, y, nullptr, T, 1, slope, 1.f, 0, 0, tx);
+  };
+  auto ln = [&](const float* a, const float* rr, const float* res, size_t g_off, size_t b_off, int C, int pre, int post,
+                float* out) -> int {
+    tts_ln_kernel<<<gRow, 64, 0, st>>>(a, rr, res, P + g_off, P + b_off, lens, T, C, pre, post, out);
+    CK(cudaGetLastError());
+    c->launches++;
+    return OVC_OK;
+  };
+#define TTS_LAUNCHED() do { CK(cudaGetLastError()); c->launches++; } while (0)
+
+  float *X = ws + W.X, *QKV = ws + W.QKV, *S = ws + W.S, *A = ws + W.A, *Y = ws + W.Y, *F = ws + W.F, *g = ws + W.g;
+  tts_speaker_kernel<<<dim3((G + 127) / 128, B), 128, 0, st>>>(P + L.emb_g, sid, L.n_speakers, G, g);
+  TTS_LAUNCHED();
+  // ---- TextEncoder (models.py:47-57)
+  tts_embed_kernel<<<gE, 256, 0, st>>>(tokens, lens, P + L.emb, L.n_vocab, T, H, sqrtf((float)H), X);
+  TTS_LAUNCHED();
+  for (int i = 0; i < L.n_layers; ++i) {
+    // MultiHeadAttention (attentions.py:262-324): QKV projection and output projection on the tensor cores
+    TRY(dense(L.qkv[i], X, QKV, 1.f));
+    tts_scores_kernel<<<dim3((T * T + 255) / 256, L.heads, B), 256, 0, st>>>(QKV, lens, P + L.relk[i], T, H, L.heads, L.window, S);
+    TTS_LAUNCHED();
+    tts_attn_out_kernel<<<gE, 256, 0, st>>>(S, QKV, lens, P + L.relv[i], T, H, L.heads, L.window, A);
+    TTS_LAUNCHED();
+    TRY(dense(L.o[i], A, Y, 1.f));
+    TRY(ln(X, Y, nullptr, L.ln1g[i], L.ln1b[i], H, 0, 0, X));                  // attentions.py:115
+    // FFN (attentions.py:439-448): conv k, relu (as the next conv's input activation), conv k
+    TRY(dense(L.ffn1[i], X, F, 1.f));
+    TRY(dense(L.ffn2[i], F, Y, 0.f));
+    TRY(ln(X, Y, nullptr, L.ln2g[i], L.ln2b[i], H, 0, 0, X));                  // attentions.py:119
+    if (i == 0) TRY(tts_tap(r, "tts.layer0", X, H));
+  }
+  TRY(tts_tap(r, "tts.x", X, H));
+  TRY(dense(L.proj, X, ws + W.STATS, 1.f));                                     // models.py:54
+  TRY(tts_tap(r, "tts.stats", ws + W.STATS, 2 * L.C));
+
+  // ---- DurationPredictor (models.py:86-100)
+  float *DX = ws + W.DX, *D1 = ws + W.D1, *D2 = ws + W.D2, *cv = ws + W.cv;
+  tts_lin_kernel<<<dim3((H + 127) / 128, B), 128, 0, st>>>(g, P + L.dp_cw, P + L.dp_cb, G, H, cv);
+  TTS_LAUNCHED();
+  tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(X, cv, lens, T, H, DX);
+  TTS_LAUNCHED();
+  TRY(dense(L.dp_c1, DX, D1, 1.f));
+  TRY(ln(D1, nullptr, nullptr, L.dp_n1g, L.dp_n1b, L.D, 1, 0, D1));
+  TRY(dense(L.dp_c2, D1, D2, 1.f));
+  TRY(ln(D2, nullptr, nullptr, L.dp_n2g, L.dp_n2b, L.D, 1, 0, D2));
+  const dim3 gT((T + 127) / 128, B);
+  tts_logw_kernel<<<gT, 128, 0, st>>>(D2, lens, P + L.dp_pw, P + L.dp_pb, T, L.D, 0, ws + W.lwd);
+  TTS_LAUNCHED();
+
+  // ---- StochasticDurationPredictor, reverse (models.py:135-143, 170-180)
+  float *SX = ws + W.SX, *XC = ws + W.XC, *HH = ws + W.HH, *Y1 = ws + W.Y1, *Y2 = ws + W.Y2;
+  auto dds = [&](int j, float* h) -> int {                                      // DDSConv.forward, modules.py:115-130
+    const DdsLayers& d = L.dds[j];
+    int dil = 1;
+    for (int i = 0; i < 3; ++i, dil *= 3) {
+      tts_dwconv_kernel<<<gE, 256, 0, st>>>(h, lens, P + d.sep_w[i], P + d.sep_b[i], T, H, dil, Y1);
+      TTS_LAUNCHED();
+      TRY(ln(Y1, nullptr, nullptr, d.n1g[i], d.n1b[i], H, 0, 1, Y1));
+      TRY(dense(d.c1x1[i], Y1, Y2, 1.f));
+      TRY(ln(Y2, nullptr, h, d.n2g[i], d.n2b[i], H, 0, 1, h));
+    }
+    return OVC_OK;
+  };
+  TRY(dense(L.sdp_pre, X, SX, 1.f));
+  tts_lin_kernel<<<dim3((H + 127) / 128, B), 128, 0, st>>>(g, P + L.sdp_cw, P + L.sdp_cb, G, H, cv);
+  TTS_LAUNCHED();
+  tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(SX, cv, lens, T, H, SX);
+  TTS_LAUNCHED();
+  TRY(dds(0, SX));
+  TRY(dense(L.sdp_proj, SX, XC, 1.f));
+  TRY(tts_tap(r, "tts.sdp_cond", XC, H));
+  float *za = ws + W.z0, *zb = ws + W.z1;
+  tts_noise_w_kernel<<<gT, 128, 0, st>>>(noise_w, seed, noise_scale_w, T, za, zb);
+  TTS_LAUNCHED();
+  for (int j = 3; j >= 1; --j) {
+    std::swap(za, zb);                                                          // Flip (modules.py:375-376)
+    tts_cf_pre_kernel<<<gE, 256, 0, st>>>(za, P + L.cf_pre_w[j], P + L.cf_pre_b[j], XC, lens, T, H, HH);
+    TTS_LAUNCHED();
+    TRY(dds(j, HH));
+    tts_cf_tail_kernel<<<gRow, 64, 0, st>>>(HH, lens, P + L.cf_pw[j], P + L.cf_pb[j], zb, T, H, 5.0f);   // tail_bound, modules.py:467
+    TTS_LAUNCHED();
+  }
+  std::swap(za, zb);
+  tts_logw_kernel<<<gT, 128, 0, st>>>(za, lens, P + L.ea, nullptr, T, 1, 1, ws + W.lws);
+  TTS_LAUNCHED();
+  // ---- durations (models.py:474-481)
+  long long* ylen = reinterpret_cast<long long*>(ws + W.ylen);
+  int* cum = reinterpret_cast<int*>(ws + W.cum);
+  tts_durations_kernel<<<(B + 63) / 64, 64, 0, st>>>(ws + W.lws, ws + W.lwd, lens, sdp_ratio, length_scale, B, T, ws + W.logw,
+                                                     ws + W.wceil, cum, ylen);
+  TTS_LAUNCHED();
+#undef TTS_LAUNCHED
+  if (c->debug) {
+    Run r1{c, st, B, T, T, lens, lens, 0.0};
+    TRY(tap(r1, "tts.logw_sdp", ws + W.lws, 1, T, T));
+    TRY(tap(r1, "tts.logw_dp", ws + W.lwd, 1, T, T));
+  }
+  CK(cudaMemcpyAsync(y_lengths, ylen, (size_t)B * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+  if (w_ceil_out) CK(cudaMemcpyAsync(w_ceil_out, ws + W.wceil, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (logw_out) CK(cudaMemcpyAsync(logw_out, ws + W.logw, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  c->tts_B = B;
+  c->tts_T = T;
+  return OVC_OK;
+}
+
+// durations -> waveform: expand m_p / logs_p along the path, sample z_p, flow reverse, generator (models.py:482-490)
+static int run_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int ragged,
+                          float* o, float* z_out, float* zp_out, cudaStream_t st) {
+  const TtsLayers& L = c->tts;
+  const int T = c->tts_T;
+  const TtsWs TW = tts_ws_layout(c, B, T);
+  const WsLayout W = ws_layout(c, B, Ymax);
+  TRY(ensure_ws(c, W, B, Ymax, st));
+  float* ws = c->d_ws;
+  const long long* ylen = reinterpret_cast<const long long*>(c->d_tts + TW.ylen);
+  Run r{c, st, B, Ymax, W.P, ylen, ragged ? ylen : nullptr, (double)B * Ymax};
+  c->launches = 0;
+  {
+    dim3 grid((W.P + 127) / 128, L.C, B);
+    tts_expand_kernel<<<grid, 128, 0, st>>>(c->d_tts + TW.STATS, reinterpret_cast<const int*>(c->d_tts + TW.cum), ylen, noise,
+                                            (long long)L.C * Ymax, Ymax, seed, noise_scale, T, L.C, Ymax, W.P, ws + W.z);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  TRY(copy_latent_out(r, W, ws, zp_out));
+  {
+    CondArgs a;   // g conditions the flow (as g_tgt) and the generator (models.py:488-489)
+    a.w = c->d_w + c->cond_w_off; a.bias = c->d_w + c->cond_b_off;
+    a.w_row = c->d_cond_wrow; a.sel = c->d_cond_sel;
+    a.g_src = c->d_tts + TW.g; a.g_tgt = c->d_tts + TW.g; a.out = ws + W.cond;
+    a.rows_out = c->cond_rows_out; a.gin = c->hp.gin_channels;
+    dim3 grid((c->cond_rows_out + 7) / 8, B);
+    cond_kernel<<<grid, 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  const float* cond = ws + W.cond;
+  TRY(run_flow(r, W, ws, true, cond));
+  TRY(copy_latent_out(r, W, ws, z_out));
+  return run_dec(r, W, ws, cond, ylen, o);
+}
+
 }  // namespace ovc
 
 // =================================================================================================
@@ -1149,6 +1518,7 @@ void ovc_destroy(ovc_ctx* c) {
   cudaSetDevice(c->device);
   if (c->d_w) cudaFree(c->d_w);
   if (c->d_ws) cudaFree(c->d_ws);
+  if (c->d_tts) cudaFree(c->d_tts);
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
   if (c->d_tcw) cudaFree(c->d_tcw);
@@ -1295,6 +1665,45 @@ int ovc_reference_encoder(ovc_ctx* c, const float* spec, int N, int T, float* ou
     CK(cudaGetLastError());
   }
   return OVC_OK;
+}
+
+int ovc_tts_info(const ovc_ctx* c, int32_t* out8) {
+  if (!c || !out8) return fail(OVC_ERR_INVALID, "null argument");
+  if (!c->finalized) return fail(OVC_ERR_STATE, "ovc_finalize_weights has not been called");
+  const TtsLayers& L = c->tts;
+  const int32_t v[8] = {L.ready ? 1 : 0, L.n_vocab, L.n_speakers, L.heads, L.n_layers, L.window, L.Fc, L.D};
+  for (int i = 0; i < 8; ++i) out8[i] = v[i];
+  return OVC_OK;
+}
+
+int ovc_tts_encode(ovc_ctx* c, const int64_t* tokens, const int64_t* x_lengths, const int64_t* sid, const float* noise_w,
+                   uint64_t seed, float noise_scale_w, float length_scale, float sdp_ratio, int B, int T, int64_t* y_lengths,
+                   float* w_ceil, float* logw, void* stream) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  if (!c->finalized) return fail(OVC_ERR_STATE, "ovc_finalize_weights has not been called");
+  if (!c->tts.ready) return fail(OVC_ERR_STATE, "the checkpoint has no TTS members (enc_p / dp / sdp / emb_g): not a V1 base speaker");
+  if (!tokens || !x_lengths || !sid || !y_lengths) return fail(OVC_ERR_INVALID, "null tensor argument");
+  if (B < 1 || T < 1) return fail(OVC_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
+  if (B > 65535 || (long long)T * T > 2000000000LL / 256) return fail(OVC_ERR_INVALID, "B %d / T %d exceed the grid limits", B, T);
+  if (!(length_scale > 0.f)) return fail(OVC_ERR_INVALID, "length_scale must be positive");
+  CK(cudaSetDevice(c->device));
+  c->ev_used = c->prof ? c->ev_used : 0;
+  return run_tts_encode(c, (const long long*)tokens, (const long long*)x_lengths, (const long long*)sid, noise_w, seed,
+                        noise_scale_w, length_scale, sdp_ratio, B, T, (long long*)y_lengths, w_ceil, logw, (cudaStream_t)stream);
+}
+
+int ovc_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int ragged, float* o,
+                   float* z, float* z_p, void* stream) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  if (!c->finalized || !c->tts.ready) return fail(OVC_ERR_STATE, "no finalized TTS checkpoint");
+  if (c->tts_B < 1) return fail(OVC_ERR_STATE, "ovc_tts_decode needs a preceding ovc_tts_encode");
+  if (B != c->tts_B) return fail(OVC_ERR_INVALID, "B = %d but the pending ovc_tts_encode had B = %d", B, c->tts_B);
+  if (!o) return fail(OVC_ERR_INVALID, "null tensor argument");
+  if (Ymax < 1) return fail(OVC_ERR_INVALID, "Ymax must be positive");
+  if ((long long)Ymax * 256 * 64 > 2000000000LL) return fail(OVC_ERR_INVALID, "Ymax %d too large for 32-bit indexing", Ymax);
+  CK(cudaSetDevice(c->device));
+  c->ev_used = c->prof ? c->ev_used : 0;
+  return run_tts_decode(c, noise, seed, noise_scale, B, Ymax, ragged, o, z, z_p, (cudaStream_t)stream);
 }
 
 int ovc_set_precision(ovc_ctx* c, int mode) {

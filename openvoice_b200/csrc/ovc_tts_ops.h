@@ -7,7 +7,7 @@
 //
 // Every function is plain C++ on raw pointers (OVC_HD = __host__ __device__ under nvcc, empty otherwise): the CUDA
 // kernels in ovc_tts.cuh are one-thread-per-element wrappers around them, and tests/hostcheck compiles the same
-// functions with g++ to check them against the oracle on the CPU box.  They do a few MFLOP per sentence (SURVEY.md
+// functions with g++ so that they can be checked on the CPU box without a GPU.  They do a few MFLOP per sentence (SURVEY.md
 // section 8 rows a12/a13: "< 0.1 % of the decoder"), so clarity wins over speed here.
 #pragma once
 #include <math.h>

@@ -61,3 +61,24 @@ def native(request):
 @pytest.fixture(scope="session")
 def native_v2():
     return get_native(True)
+
+
+_tts_cache = {}
+
+
+def get_native_tts():
+    """NativeSynthesizer on the synthetic V1 base-speaker checkpoint (enc_p / dp / sdp / emb_g + enc_q / flow / dec)."""
+    import copy
+    from oracle import tts_oracle as T
+    from oracle import vc_oracle as O
+    from openvoice_b200.api import NativeSynthesizer
+    from openvoice_b200.utils import HParams
+    if "m" not in _tts_cache:
+        hp = copy.deepcopy(O.DEFAULT_HPARAMS)
+        hp["data"]["n_speakers"] = T.TTS_HPARAMS["n_speakers"]
+        m = NativeSynthesizer(HParams(**hp), "cuda:0")
+        missing, unexpected = m.load_state_dict(T.synthetic_tts_state_dict())
+        assert not missing, missing
+        assert all(k.startswith("sdp.flows.1.") for k in unexpected), unexpected   # never run in reverse (models.py:172)
+        _tts_cache["m"] = m
+    return _tts_cache["m"]
