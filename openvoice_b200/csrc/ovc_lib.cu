@@ -106,9 +106,12 @@ struct TtsLayers {
   bool ready = false;
   int n_vocab = 0, n_speakers = 0, H = 0, C = 0, Fc = 0, heads = 0, n_layers = 0, window = 0, D = 0;
   size_t emb = 0, emb_g = 0;
-  std::vector<TcLayer> qkv, o, ffn1, ffn2;
+  struct Fp32Dense { size_t w = 0, b = 0; int Cin = 0, K = 0, N = 0; };   // k = 3 convs kept on the CUDA cores, w [K][Cin][N]
+  std::vector<TcLayer> qkv, o;
+  std::vector<Fp32Dense> ffn1, ffn2;
   std::vector<size_t> relk, relv, ln1g, ln1b, ln2g, ln2b;
-  TcLayer proj, dp_c1, dp_c2, sdp_pre, sdp_proj;
+  TcLayer proj, sdp_pre, sdp_proj;
+  Fp32Dense dp_c1, dp_c2;
   size_t dp_n1g = 0, dp_n1b = 0, dp_n2g = 0, dp_n2b = 0, dp_pw = 0, dp_pb = 0, dp_cw = 0, dp_cb = 0, sdp_cw = 0, sdp_cb = 0,
          ea = 0;               // ea: {m[0], logs[0]} of sdp.flows.0
   DdsLayers dds[4];            // 0: sdp.convs, j = 1..3: sdp.flows.{2j+1}.convs (flows.1 is never run in reverse, models.py:172)
@@ -425,6 +428,22 @@ static int pack_tts(ovc_ctx* c) {
                    [&](int n) { return b->data[n]; });
   };
 
+  // dense conv kept in fp32: transposed to [K][Cin][N] for coalesced weight reads (ovc_tts_ops.h dense_at)
+  auto dense32 = [&](const std::string& prefix, int cout, int cin, int k) -> TtsLayers::Fp32Dense {
+    TtsLayers::Fp32Dense d;
+    const HostTensor* w = get(prefix + ".weight", {cout, cin, k});
+    const HostTensor* b = get(prefix + ".bias", {cout});
+    if (!w || !b) return d;
+    HostTensor t;
+    t.shape = {k, cin, cout};
+    t.data.resize(w->data.size());
+    for (int n = 0; n < cout; ++n)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int tap = 0; tap < k; ++tap) t.data[((size_t)tap * cin + ci) * cout + n] = w->data[((size_t)n * cin + ci) * k + tap];
+    d.w = put(&t); d.b = put(b); d.Cin = cin; d.K = k; d.N = cout;
+    return d;
+  };
+
   const HostTensor* emb = get("enc_p.emb.weight", {-1, -1});
   if (!emb) return fail(OVC_ERR_MISSING, "%s", err.c_str());
   L.n_vocab = (int)emb->shape[0];
@@ -444,7 +463,7 @@ static int pack_tts(ovc_ctx* c) {
   const int fk = (int)f10->shape[2];
   L.D = (int)dp1->shape[0];
   L.n_speakers = (int)eg->shape[0];
-  if (L.heads < 1 || L.heads * dk != H || fk % 2 == 0 || H % 32 || L.Fc % 32 || L.D % 32 || (2 * L.C) % 32)
+  if (L.heads < 1 || L.heads * dk != H || fk % 2 == 0 || H % 32 || (2 * L.C) % 32)
     return fail(OVC_ERR_INVALID, "unsupported TTS geometry (H %d, heads %d, filter %d, ffn kernel %d, dp filter %d)", H, L.heads,
                 L.Fc, fk, L.D);
   while (find(c, "enc_p.encoder.attn_layers." + std::to_string(L.n_layers) + ".conv_q.weight")) ++L.n_layers;
@@ -471,13 +490,13 @@ static int pack_tts(ovc_ctx* c) {
     L.ln1b.push_back(put(get(e + "norm_layers_1." + std::to_string(i) + ".beta", {H})));
     L.ln2g.push_back(put(get(e + "norm_layers_2." + std::to_string(i) + ".gamma", {H})));
     L.ln2b.push_back(put(get(e + "norm_layers_2." + std::to_string(i) + ".beta", {H})));
-    L.ffn1.push_back(dense(e + "ffn_layers." + std::to_string(i) + ".conv_1", L.Fc, H, fk));
-    L.ffn2.push_back(dense(e + "ffn_layers." + std::to_string(i) + ".conv_2", H, L.Fc, fk));
+    L.ffn1.push_back(dense32(e + "ffn_layers." + std::to_string(i) + ".conv_1", L.Fc, H, fk));
+    L.ffn2.push_back(dense32(e + "ffn_layers." + std::to_string(i) + ".conv_2", H, L.Fc, fk));
   }
   L.proj = dense("enc_p.proj", 2 * L.C, H, 1);
   // DurationPredictor
-  L.dp_c1 = dense("dp.conv_1", L.D, H, 3);
-  L.dp_c2 = dense("dp.conv_2", L.D, L.D, 3);
+  L.dp_c1 = dense32("dp.conv_1", L.D, H, 3);
+  L.dp_c2 = dense32("dp.conv_2", L.D, L.D, 3);
   L.dp_n1g = put(get("dp.norm_1.gamma", {L.D})); L.dp_n1b = put(get("dp.norm_1.beta", {L.D}));
   L.dp_n2g = put(get("dp.norm_2.gamma", {L.D})); L.dp_n2b = put(get("dp.norm_2.beta", {L.D}));
   L.dp_pw = put(get("dp.proj.weight", {1, L.D, 1})); L.dp_pb = put(get("dp.proj.bias", {1}));
@@ -897,10 +916,10 @@ static int prof_end(Run& r, int variant, int family, double flops, double bytes)
   c->ev_family.push_back(family);
   return OVC_OK;
 }
-enum { V_TC128 = -1, V_TC64 = -2, V_TC32 = -3, V_TRANSPOSE = -4 };
+enum { V_TC128 = -1, V_TC64 = -2, V_TC32 = -3, V_TRANSPOSE = -4, V_TTS_DENSE = -5 };
 static const char* variant_name(int v) {
   if (v >= 0) return kInfo[v].name;
-  return v == V_TC128 ? "TC3_N128" : v == V_TC64 ? "TC3_N64" : v == V_TC32 ? "TC3_N32" : "TRANSPOSE";
+  return v == V_TC128 ? "TC3_N128" : v == V_TC64 ? "TC3_N64" : v == V_TC32 ? "TC3_N32" : v == V_TTS_DENSE ? "TTS_DENSE32" : "TRANSPOSE";
 }
 
 // one conv on the tensor cores (3xTF32 / TF32), channels-last in/out.  t_len / mul are in INPUT steps.
@@ -1336,6 +1355,13 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
   auto dense = [&](const TcLayer& lay, const float* x, float* y, float slope) -> int {
     return launch_tc(r, lay, x, y, nullptr, T, 1, slope, 1.f, 0, 0, tx);
   };
+  auto dense32 = [&](const TtsLayers::Fp32Dense& d, const float* x, float* y, int relu_in) -> int {
+    TRY(prof_begin(r));
+    tts_dense_kernel<<<dim3((T * d.N + 255) / 256, B), 256, 0, st>>>(x, lens, P + d.w, P + d.b, T, d.Cin, d.K, d.N, relu_in, y);
+    CK(cudaGetLastError());
+    c->launches++;
+    return prof_end(r, V_TTS_DENSE, 0, 2.0 * d.Cin * d.K * d.N * (double)B * T, 4.0 * (d.Cin + d.N) * (double)B * T);
+  };
   auto ln = [&](const float* a, const float* rr, const float* res, size_t g_off, size_t b_off, int C, int pre, int post,
                 float* out) -> int {
     tts_ln_kernel<<<gRow, 64, 0, st>>>(a, rr, res, P + g_off, P + b_off, lens, T, C, pre, post, out);
@@ -1360,9 +1386,9 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
     TTS_LAUNCHED();
     TRY(dense(L.o[i], A, Y, 1.f));
     TRY(ln(X, Y, nullptr, L.ln1g[i], L.ln1b[i], H, 0, 0, X));                  // attentions.py:115
-    // FFN (attentions.py:439-448): conv k, relu (as the next conv's input activation), conv k
-    TRY(dense(L.ffn1[i], X, F, 1.f));
-    TRY(dense(L.ffn2[i], F, Y, 0.f));
+    // FFN (attentions.py:439-448): conv k, relu (as the next conv's input activation), conv k -- fp32 CUDA cores
+    TRY(dense32(L.ffn1[i], X, F, 0));
+    TRY(dense32(L.ffn2[i], F, Y, 1));
     TRY(ln(X, Y, nullptr, L.ln2g[i], L.ln2b[i], H, 0, 0, X));                  // attentions.py:119
     if (i == 0) TRY(tts_tap(r, "tts.layer0", X, H));
   }
@@ -1376,9 +1402,9 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
   TTS_LAUNCHED();
   tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(X, cv, lens, T, H, DX);
   TTS_LAUNCHED();
-  TRY(dense(L.dp_c1, DX, D1, 1.f));
+  TRY(dense32(L.dp_c1, DX, D1, 0));
   TRY(ln(D1, nullptr, nullptr, L.dp_n1g, L.dp_n1b, L.D, 1, 0, D1));
-  TRY(dense(L.dp_c2, D1, D2, 1.f));
+  TRY(dense32(L.dp_c2, D1, D2, 0));
   TRY(ln(D2, nullptr, nullptr, L.dp_n2g, L.dp_n2b, L.D, 1, 0, D2));
   const dim3 gT((T + 127) / 128, B);
   tts_logw_kernel<<<gT, 128, 0, st>>>(D2, lens, P + L.dp_pw, P + L.dp_pb, T, L.D, 0, ws + W.lwd);

@@ -1,7 +1,8 @@
 // CUDA wrappers of the TTS element functions (ovc_tts_ops.h): one thread per output element / row.
 // Text-side tensors are channels-last [B][T][C]; `lens` = token counts (x_lengths, models.py:467); threads at or
-// past an utterance's length do nothing (the reference's x_mask).  The dense channel contractions between these
-// kernels (QKV / out projections, FFN, DurationPredictor convs, DDSConv 1x1) run on tcconv (ovc_tcconv.cuh).
+// past an utterance's length do nothing (the reference's x_mask).  The 1x1 channel contractions between these kernels
+// (QKV / attention-out / stats projections, SDP pre / proj, DDSConv 1x1) run on the tensor-core conv (ovc_tcconv.cuh);
+// the four k = 3 convs with long contractions (FFN, DurationPredictor) stay in fp32 on the CUDA cores (tts_dense_kernel).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -63,6 +64,17 @@ __global__ void tts_attn_out_kernel(const float* scores, const float* qkv, const
   const int dk = H / heads, h = ch / dk, d = ch % dk;
   out[((size_t)b * T + i) * H + ch] = ovc_tts::attn_out(scores + (((size_t)b * heads + h) * T + i) * T, qkv + (size_t)b * T * 3 * H,
                                                           3 * H, H, dk, h, i, d, len, rel_v, window);
+}
+
+// fp32 dense 'same' conv (FFN / DurationPredictor k = 3 layers), w [K][Cin][N]      grid (ceil(T*N/256), B)
+__global__ void tts_dense_kernel(const float* x, const long long* lens, const float* w, const float* bias, int T, int Cin,
+                                 int K, int N, int relu_in, float* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (idx >= T * N) return;
+  const int t = idx / N, n = idx % N;
+  const int len = tts_len(lens, b, T);
+  if (t >= len) return;
+  out[((size_t)b * T + t) * N + n] = ovc_tts::dense_at(x + (size_t)b * T * Cin, w, bias, Cin, K, N, t, n, len, relu_in);
 }
 
 // grid (ceil(T*C/256), B)

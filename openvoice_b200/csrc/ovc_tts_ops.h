@@ -102,6 +102,29 @@ OVC_HD float attn_out(const float* scores_row, const float* qkv_b, int ld, int H
   return acc;
 }
 
+// ---- dense 'same' conv, one output element, plain fp32 FMA chain               attentions.py:439-448, models.py:90-96
+// The k = 3 convs of the FFN and the DurationPredictor contract over up to 3 * 768 terms; on the tensor cores the
+// TMEM accumulator's truncation costs ~3e-5 of the row there, which the spline inverses of the SDP amplify
+// into duration flips -- so these four layers stay on the CUDA cores.  w is stored [K][Cin][N] (n contiguous: a
+// warp of consecutive n reads coalesced weights and one broadcast activation).  relu_in: relu on the input rows.
+OVC_HD float dense_at(const float* x_b, const float* w, const float* bias, int Cin, int K, int N, int t, int n, int len,
+                      int relu_in) {
+  float acc = bias[n];
+  const int pad = (K - 1) / 2;
+  for (int k = 0; k < K; ++k) {
+    const int tt = t + k - pad;
+    if (tt < 0 || tt >= len) continue;
+    const float* xr = x_b + (size_t)tt * Cin;
+    const float* wk = w + (size_t)k * Cin * N + n;
+    for (int c = 0; c < Cin; ++c) {
+      float v = xr[c];
+      if (relu_in) v = v > 0.f ? v : 0.f;
+      acc += v * wk[(size_t)c * N];
+    }
+  }
+  return acc;
+}
+
 // ---- DDSConv depthwise dilated conv, one output element                       modules.py:100-108,118
 // x [T][C] rows (masked at len), w [C][3], 'same' padding = dilation
 OVC_HD float dwconv_at(const float* x_b, const float* w, const float* bias, int C, int t, int c, int len, int dil) {

@@ -48,6 +48,16 @@ void hc_dwconv(const float* x, const long long* lens, const float* w, const floa
             t < lens[b] ? dwconv_at(x + (size_t)b * T * C, w, bias, C, t, c, (int)lens[b], dil) : 0.f;
 }
 
+// w [K][Cin][N]
+void hc_dense(const float* x, const long long* lens, const float* w, const float* bias, int B, int T, int Cin, int K, int N,
+              int relu_in, float* out) {
+  for (int b = 0; b < B; ++b)
+    for (int t = 0; t < T; ++t)
+      for (int n = 0; n < N; ++n)
+        out[((size_t)b * T + t) * N + n] =
+            t < lens[b] ? dense_at(x + (size_t)b * T * Cin, w, bias, Cin, K, N, t, n, (int)lens[b], relu_in) : 0.f;
+}
+
 void hc_spline_inverse(const float* x, const float* p, int n, float scale, float bound, float* out) {
   for (int i = 0; i < n; ++i) out[i] = rq_spline_inverse(x[i], p + (size_t)i * NP, scale, bound);
 }

@@ -80,6 +80,14 @@ class Ops:
         self.lib.hc_dwconv(fp(x), fp(ln), fp(ww), fp(bb), x.shape[0], x.shape[1], x.shape[2], dil, fp(out))
         return out
 
+    def dense(self, x, lens, w, bias, relu_in=False):
+        B, Tn, Cin = x.shape
+        N, _, K = w.shape
+        out = np.empty((B, Tn, N), np.float32)
+        ln, wt, bb = np.ascontiguousarray(lens.numpy()), f32(w.permute(2, 1, 0)), f32(bias)     # [K][Cin][N]
+        self.lib.hc_dense(fp(x), fp(ln), fp(wt), fp(bb), B, Tn, Cin, K, N, 1 if relu_in else 0, fp(out))
+        return out
+
     def convflow_tail(self, h, lens, pw, pb, x1, bound):
         out = np.empty_like(x1)
         ln, w, b = np.ascontiguousarray(lens.numpy()), f32(pw.reshape(pw.shape[0], -1)), f32(pb)
@@ -145,6 +153,18 @@ def test_dwconv(ops):
         assert np.abs(ops.dwconv(cl(x), lens, w, b, dil) - cl(ref)).max() < 2e-6
 
 
+def test_dense_same_conv(ops):
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 96, 21, generator=g)
+    w, b = torch.randn(40, 96, 3, generator=g) / 17, torch.randn(40, generator=g)
+    lens = torch.tensor([21, 8])
+    mask = V.sequence_mask(lens, 21, torch.float32)
+    ref = F.conv1d(torch.relu(x * mask), w, b, padding=1) * mask
+    assert np.abs(ops.dense(cl(x), lens, w, b, relu_in=True) - cl(ref)).max() < 3e-6
+    ref = F.conv1d(x * mask, w, b, padding=1) * mask
+    assert np.abs(ops.dense(cl(x), lens, w, b) - cl(ref)).max() < 3e-6
+
+
 def test_spline_inverse(hc):
     g = torch.Generator().manual_seed(4)
     n = 5000
@@ -207,17 +227,17 @@ def host_front(ops, sd, tokens, lens, sid, noise_w, noise_scale_w, length_scale,
         e = "enc_p.encoder"
         x = ops.ln(x, y, None, sd[f"{e}.norm_layers_1.{i}.gamma"], sd[f"{e}.norm_layers_1.{i}.beta"])
         f = f"{e}.ffn_layers.{i}"
-        h1 = conv_cl(x, sd[f"{f}.conv_1.weight"], sd[f"{f}.conv_1.bias"], pad=1, lens=lens)
-        y = conv_cl(h1, sd[f"{f}.conv_2.weight"], sd[f"{f}.conv_2.bias"], pad=1, relu_in=True, lens=lens)
+        h1 = ops.dense(x, lens, sd[f"{f}.conv_1.weight"], sd[f"{f}.conv_1.bias"])
+        y = ops.dense(h1, lens, sd[f"{f}.conv_2.weight"], sd[f"{f}.conv_2.bias"], relu_in=True)
         x = ops.ln(x, y, None, sd[f"{e}.norm_layers_2.{i}.gamma"], sd[f"{e}.norm_layers_2.{i}.beta"])
     stats = conv_cl(x, sd["enc_p.proj.weight"], sd["enc_p.proj.bias"], lens=lens)
     g = sd["emb_g.weight"][sid]                                                  # [B,gin]
     # duration predictor
     cv = g @ sd["dp.cond.weight"][:, :, 0].t() + sd["dp.cond.bias"]
     d = x + cv[:, None, :].numpy()
-    d = conv_cl(d, sd["dp.conv_1.weight"], sd["dp.conv_1.bias"], pad=1, lens=lens)
+    d = ops.dense(np.ascontiguousarray(d, dtype=np.float32), lens, sd["dp.conv_1.weight"], sd["dp.conv_1.bias"])
     d = ops.ln(d, None, None, sd["dp.norm_1.gamma"], sd["dp.norm_1.beta"], pre=1)
-    d = conv_cl(d, sd["dp.conv_2.weight"], sd["dp.conv_2.bias"], pad=1, lens=lens)
+    d = ops.dense(d, lens, sd["dp.conv_2.weight"], sd["dp.conv_2.bias"])
     d = ops.ln(d, None, None, sd["dp.norm_2.gamma"], sd["dp.norm_2.beta"], pre=1)
     logw_d = (torch.from_numpy(d) @ sd["dp.proj.weight"][0, :, 0] + sd["dp.proj.bias"]).numpy()
 
