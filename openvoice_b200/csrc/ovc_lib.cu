@@ -106,7 +106,9 @@ struct TtsLayers {
   bool ready = false;
   int n_vocab = 0, n_speakers = 0, H = 0, C = 0, Fc = 0, heads = 0, n_layers = 0, window = 0, D = 0;
   size_t emb = 0, emb_g = 0;
-  struct Fp32Dense { size_t w = 0, b = 0; int Cin = 0, K = 0, N = 0; };   // k = 3 convs kept on the CUDA cores, w [K][Cin][N]
+  // k = 3 convs kept on the CUDA cores: the FFMA2 conv kernel on a [C][T] copy when the shape fits a variant
+  // (k 3, N % 64 == 0: every released checkpoint), else the one-thread-per-output kernel on w [K][Cin][N]
+  struct Fp32Dense { size_t w = 0, b = 0; int Cin = 0, K = 0, N = 0; bool fast = false; ConvLayer cl; };
   std::vector<TcLayer> qkv, o;
   std::vector<Fp32Dense> ffn1, ffn2;
   std::vector<size_t> relk, relv, ln1g, ln1b, ln2g, ln2b;
@@ -441,6 +443,12 @@ static int pack_tts(ovc_ctx* c) {
       for (int ci = 0; ci < cin; ++ci)
         for (int tap = 0; tap < k; ++tap) t.data[((size_t)tap * cin + ci) * cout + n] = w->data[((size_t)n * cin + ci) * k + tap];
     d.w = put(&t); d.b = put(b); d.Cin = cin; d.K = k; d.N = cout;
+    if (k == 3 && cout % 64 == 0 && cin % 8 == 0) {
+      d.cl = pack_conv(c, cout % 128 == 0 ? V_A_K3D1 : V_B_K3D1, cout, cin,
+                       [&](int r, int ci, int tap) { return w->data[((size_t)r * cin + ci) * k + tap]; },
+                       [&](int r) { return b->data[r]; }, cout, k, cout);
+      d.fast = true;
+    }
     return d;
   };
 
@@ -916,10 +924,23 @@ static int prof_end(Run& r, int variant, int family, double flops, double bytes)
   c->ev_family.push_back(family);
   return OVC_OK;
 }
-enum { V_TC128 = -1, V_TC64 = -2, V_TC32 = -3, V_TRANSPOSE = -4, V_TTS_DENSE = -5 };
+enum { V_TC128 = -1, V_TC64 = -2, V_TC32 = -3, V_TRANSPOSE = -4, V_TTS_DENSE = -5, V_TTS_LN = -6, V_TTS_SCORES = -7,
+       V_TTS_ATTN = -8, V_TTS_DW = -9, V_TTS_SPLINE = -10, V_TTS_MISC = -11 };
 static const char* variant_name(int v) {
   if (v >= 0) return kInfo[v].name;
-  return v == V_TC128 ? "TC3_N128" : v == V_TC64 ? "TC3_N64" : v == V_TC32 ? "TC3_N32" : v == V_TTS_DENSE ? "TTS_DENSE32" : "TRANSPOSE";
+  switch (v) {
+    case V_TC128: return "TC3_N128";
+    case V_TC64: return "TC3_N64";
+    case V_TC32: return "TC3_N32";
+    case V_TTS_DENSE: return "TTS_DENSE32";
+    case V_TTS_LN: return "TTS_LAYERNORM";
+    case V_TTS_SCORES: return "TTS_SCORES";
+    case V_TTS_ATTN: return "TTS_ATTN_OUT";
+    case V_TTS_DW: return "TTS_DWCONV";
+    case V_TTS_SPLINE: return "TTS_SPLINE";
+    case V_TTS_MISC: return "TTS_MISC";
+    default: return "TRANSPOSE";
+  }
 }
 
 // one conv on the tensor cores (3xTF32 / TF32), channels-last in/out.  t_len / mul are in INPUT steps.
@@ -1303,7 +1324,9 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
 // V1 TTS front half (SynthesizerTrn.infer, models.py:467-490)
 // ---------------------------------------------------------------------------------------------
 struct TtsWs {   // float offsets into c->d_tts; rows R = B * T, channels-last
-  size_t g, cv, X, QKV, S, A, Y, F, STATS, DX, D1, D2, SX, XC, HH, Y1, Y2, z0, z1, lws, lwd, logw, wceil, cum, ylen, total;
+  size_t g, cv, X, QKV, S, A, Y, F, STATS, DX, D1, D2, SX, XC, HH, Y1, Y2, z0, z1, lws, lwd, logw, wceil, cum, ylen, CT0, CT1, CT2,
+      total;
+  int P;   // time pitch of the [C][P] copies (multiple of 4)
 };
 static TtsWs tts_ws_layout(const ovc_ctx* c, int B, int T) {
   const TtsLayers& L = c->tts;
@@ -1320,6 +1343,9 @@ static TtsWs tts_ws_layout(const ovc_ctx* c, int B, int T) {
   W.z0 = take(R); W.z1 = take(R); W.lws = take(R); W.lwd = take(R); W.logw = take(R); W.wceil = take(R);
   W.cum = take(R);                 // int32
   W.ylen = take((size_t)2 * B + 4);   // int64
+  W.P = (int)round_up((size_t)T, 4);
+  const size_t widest = (size_t)std::max(std::max(L.Fc, L.D), L.H);
+  W.CT0 = take((size_t)B * widest * W.P); W.CT1 = take((size_t)B * widest * W.P); W.CT2 = take((size_t)B * widest * W.P);
   W.total = o;
   return W;
 }
@@ -1355,7 +1381,39 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
   auto dense = [&](const TcLayer& lay, const float* x, float* y, float slope) -> int {
     return launch_tc(r, lay, x, y, nullptr, T, 1, slope, 1.f, 0, 0, tx);
   };
+  // ---- the k = 3 convs in fp32.  Fast path: rows -> [C][P], FFMA2 conv kernel(s), -> rows; a chain of convs (the FFN)
+  // stays in [C][P] between its members.  relu before a conv = its input leaky-relu with slope 0.
+  Run rc{c, st, B, T, W.P, lens, lens, (double)B * T};
+  float* CT[3] = {ws + W.CT0, ws + W.CT1, ws + W.CT2};
+  auto to_ct = [&](const float* x, int C, float* out) -> int {
+    TRY(prof_begin(r));
+    tts_to_ct_kernel<<<dim3((W.P + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st>>>(x, lens, T, C, W.P, out);
+    CK(cudaGetLastError());
+    c->launches++;
+    return prof_end(r, V_TRANSPOSE, 0, 0.0, 8.0 * C * (double)B * T);
+  };
+  auto from_ct = [&](const float* in, int C, float* out) -> int {
+    TRY(prof_begin(r));
+    tts_from_ct_kernel<<<dim3((W.P + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st>>>(in, lens, T, C, W.P, out);
+    CK(cudaGetLastError());
+    c->launches++;
+    return prof_end(r, V_TRANSPOSE, 0, 0.0, 8.0 * C * (double)B * T);
+  };
+  auto conv_ct = [&](const TtsLayers::Fp32Dense& d, const float* x, float* y, int relu_in) -> int {
+    ConvArgs a{};
+    a.x = x; a.x_bs = (long long)d.Cin * W.P; a.x_pitch = W.P;
+    a.bias = P + d.cl.b_off; a.bias_bs = 0;
+    a.y = y; a.y_bs = (long long)d.N * W.P; a.y_pitch = W.P;
+    a.lens_in = lens; a.lens_out = lens; a.mul_in = 1; a.mul_out = 1;
+    a.slope = relu_in ? 0.f : 1.f; a.scale = 1.f;
+    return launch(rc, d.cl, a, T);
+  };
   auto dense32 = [&](const TtsLayers::Fp32Dense& d, const float* x, float* y, int relu_in) -> int {
+    if (d.fast) {
+      TRY(to_ct(x, d.Cin, CT[0]));
+      TRY(conv_ct(d, CT[0], CT[1], relu_in));
+      return from_ct(CT[1], d.N, y);
+    }
     TRY(prof_begin(r));
     tts_dense_kernel<<<dim3((T * d.N + 255) / 256, B), 256, 0, st>>>(x, lens, P + d.w, P + d.b, T, d.Cin, d.K, d.N, relu_in, y);
     CK(cudaGetLastError());
@@ -1364,31 +1422,42 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
   };
   auto ln = [&](const float* a, const float* rr, const float* res, size_t g_off, size_t b_off, int C, int pre, int post,
                 float* out) -> int {
+    TRY(prof_begin(r));
     tts_ln_kernel<<<gRow, 64, 0, st>>>(a, rr, res, P + g_off, P + b_off, lens, T, C, pre, post, out);
     CK(cudaGetLastError());
     c->launches++;
-    return OVC_OK;
+    return prof_end(r, V_TTS_LN, 0, 0.0, 0.0);
   };
-#define TTS_LAUNCHED() do { CK(cudaGetLastError()); c->launches++; } while (0)
+#define TTS_RUN(V, ...)                       \
+  do {                                        \
+    TRY(prof_begin(r));                       \
+    __VA_ARGS__;                              \
+    CK(cudaGetLastError());                   \
+    c->launches++;                            \
+    TRY(prof_end(r, V, 0, 0.0, 0.0));         \
+  } while (0)
 
   float *X = ws + W.X, *QKV = ws + W.QKV, *S = ws + W.S, *A = ws + W.A, *Y = ws + W.Y, *F = ws + W.F, *g = ws + W.g;
-  tts_speaker_kernel<<<dim3((G + 127) / 128, B), 128, 0, st>>>(P + L.emb_g, sid, L.n_speakers, G, g);
-  TTS_LAUNCHED();
+  TTS_RUN(V_TTS_MISC, tts_speaker_kernel<<<dim3((G + 127) / 128, B), 128, 0, st>>>(P + L.emb_g, sid, L.n_speakers, G, g));
   // ---- TextEncoder (models.py:47-57)
-  tts_embed_kernel<<<gE, 256, 0, st>>>(tokens, lens, P + L.emb, L.n_vocab, T, H, sqrtf((float)H), X);
-  TTS_LAUNCHED();
+  TTS_RUN(V_TTS_MISC, tts_embed_kernel<<<gE, 256, 0, st>>>(tokens, lens, P + L.emb, L.n_vocab, T, H, sqrtf((float)H), X));
   for (int i = 0; i < L.n_layers; ++i) {
     // MultiHeadAttention (attentions.py:262-324): QKV projection and output projection on the tensor cores
     TRY(dense(L.qkv[i], X, QKV, 1.f));
-    tts_scores_kernel<<<dim3((T * T + 255) / 256, L.heads, B), 256, 0, st>>>(QKV, lens, P + L.relk[i], T, H, L.heads, L.window, S);
-    TTS_LAUNCHED();
-    tts_attn_out_kernel<<<gE, 256, 0, st>>>(S, QKV, lens, P + L.relv[i], T, H, L.heads, L.window, A);
-    TTS_LAUNCHED();
+    TTS_RUN(V_TTS_SCORES, tts_scores_kernel<<<dim3((T * T + 255) / 256, L.heads, B), 256, 0, st>>>(QKV, lens, P + L.relk[i], T, H, L.heads, L.window, S));
+    TTS_RUN(V_TTS_ATTN, tts_attn_out_kernel<<<gE, 256, 0, st>>>(S, QKV, lens, P + L.relv[i], T, H, L.heads, L.window, A));
     TRY(dense(L.o[i], A, Y, 1.f));
     TRY(ln(X, Y, nullptr, L.ln1g[i], L.ln1b[i], H, 0, 0, X));                  // attentions.py:115
     // FFN (attentions.py:439-448): conv k, relu (as the next conv's input activation), conv k -- fp32 CUDA cores
-    TRY(dense32(L.ffn1[i], X, F, 0));
-    TRY(dense32(L.ffn2[i], F, Y, 1));
+    if (L.ffn1[i].fast && L.ffn2[i].fast) {
+      TRY(to_ct(X, H, CT[0]));
+      TRY(conv_ct(L.ffn1[i], CT[0], CT[1], 0));
+      TRY(conv_ct(L.ffn2[i], CT[1], CT[2], 1));
+      TRY(from_ct(CT[2], H, Y));
+    } else {
+      TRY(dense32(L.ffn1[i], X, F, 0));
+      TRY(dense32(L.ffn2[i], F, Y, 1));
+    }
     TRY(ln(X, Y, nullptr, L.ln2g[i], L.ln2b[i], H, 0, 0, X));                  // attentions.py:119
     if (i == 0) TRY(tts_tap(r, "tts.layer0", X, H));
   }
@@ -1398,17 +1467,14 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
 
   // ---- DurationPredictor (models.py:86-100)
   float *DX = ws + W.DX, *D1 = ws + W.D1, *D2 = ws + W.D2, *cv = ws + W.cv;
-  tts_lin_kernel<<<dim3((H + 127) / 128, B), 128, 0, st>>>(g, P + L.dp_cw, P + L.dp_cb, G, H, cv);
-  TTS_LAUNCHED();
-  tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(X, cv, lens, T, H, DX);
-  TTS_LAUNCHED();
+  TTS_RUN(V_TTS_MISC, tts_lin_kernel<<<dim3((H + 127) / 128, B), 128, 0, st>>>(g, P + L.dp_cw, P + L.dp_cb, G, H, cv));
+  TTS_RUN(V_TTS_MISC, tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(X, cv, lens, T, H, DX));
   TRY(dense32(L.dp_c1, DX, D1, 0));
   TRY(ln(D1, nullptr, nullptr, L.dp_n1g, L.dp_n1b, L.D, 1, 0, D1));
   TRY(dense32(L.dp_c2, D1, D2, 0));
   TRY(ln(D2, nullptr, nullptr, L.dp_n2g, L.dp_n2b, L.D, 1, 0, D2));
   const dim3 gT((T + 127) / 128, B);
-  tts_logw_kernel<<<gT, 128, 0, st>>>(D2, lens, P + L.dp_pw, P + L.dp_pb, T, L.D, 0, ws + W.lwd);
-  TTS_LAUNCHED();
+  TTS_RUN(V_TTS_MISC, tts_logw_kernel<<<gT, 128, 0, st>>>(D2, lens, P + L.dp_pw, P + L.dp_pb, T, L.D, 0, ws + W.lwd));
 
   // ---- StochasticDurationPredictor, reverse (models.py:135-143, 170-180)
   float *SX = ws + W.SX, *XC = ws + W.XC, *HH = ws + W.HH, *Y1 = ws + W.Y1, *Y2 = ws + W.Y2;
@@ -1416,8 +1482,7 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
     const DdsLayers& d = L.dds[j];
     int dil = 1;
     for (int i = 0; i < 3; ++i, dil *= 3) {
-      tts_dwconv_kernel<<<gE, 256, 0, st>>>(h, lens, P + d.sep_w[i], P + d.sep_b[i], T, H, dil, Y1);
-      TTS_LAUNCHED();
+      TTS_RUN(V_TTS_DW, tts_dwconv_kernel<<<gE, 256, 0, st>>>(h, lens, P + d.sep_w[i], P + d.sep_b[i], T, H, dil, Y1));
       TRY(ln(Y1, nullptr, nullptr, d.n1g[i], d.n1b[i], H, 0, 1, Y1));
       TRY(dense(d.c1x1[i], Y1, Y2, 1.f));
       TRY(ln(Y2, nullptr, h, d.n2g[i], d.n2b[i], H, 0, 1, h));
@@ -1425,34 +1490,27 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
     return OVC_OK;
   };
   TRY(dense(L.sdp_pre, X, SX, 1.f));
-  tts_lin_kernel<<<dim3((H + 127) / 128, B), 128, 0, st>>>(g, P + L.sdp_cw, P + L.sdp_cb, G, H, cv);
-  TTS_LAUNCHED();
-  tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(SX, cv, lens, T, H, SX);
-  TTS_LAUNCHED();
+  TTS_RUN(V_TTS_MISC, tts_lin_kernel<<<dim3((H + 127) / 128, B), 128, 0, st>>>(g, P + L.sdp_cw, P + L.sdp_cb, G, H, cv));
+  TTS_RUN(V_TTS_MISC, tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(SX, cv, lens, T, H, SX));
   TRY(dds(0, SX));
   TRY(dense(L.sdp_proj, SX, XC, 1.f));
   TRY(tts_tap(r, "tts.sdp_cond", XC, H));
   float *za = ws + W.z0, *zb = ws + W.z1;
-  tts_noise_w_kernel<<<gT, 128, 0, st>>>(noise_w, seed, noise_scale_w, T, za, zb);
-  TTS_LAUNCHED();
+  TTS_RUN(V_TTS_MISC, tts_noise_w_kernel<<<gT, 128, 0, st>>>(noise_w, seed, noise_scale_w, T, za, zb));
   for (int j = 3; j >= 1; --j) {
     std::swap(za, zb);                                                          // Flip (modules.py:375-376)
-    tts_cf_pre_kernel<<<gE, 256, 0, st>>>(za, P + L.cf_pre_w[j], P + L.cf_pre_b[j], XC, lens, T, H, HH);
-    TTS_LAUNCHED();
+    TTS_RUN(V_TTS_MISC, tts_cf_pre_kernel<<<gE, 256, 0, st>>>(za, P + L.cf_pre_w[j], P + L.cf_pre_b[j], XC, lens, T, H, HH));
     TRY(dds(j, HH));
-    tts_cf_tail_kernel<<<gRow, 64, 0, st>>>(HH, lens, P + L.cf_pw[j], P + L.cf_pb[j], zb, T, H, 5.0f);   // tail_bound, modules.py:467
-    TTS_LAUNCHED();
+    TTS_RUN(V_TTS_SPLINE, tts_cf_tail_kernel<<<gRow, 64, 0, st>>>(HH, lens, P + L.cf_pw[j], P + L.cf_pb[j], zb, T, H, 5.0f));   // tail_bound, modules.py:467
   }
   std::swap(za, zb);
-  tts_logw_kernel<<<gT, 128, 0, st>>>(za, lens, P + L.ea, nullptr, T, 1, 1, ws + W.lws);
-  TTS_LAUNCHED();
+  TTS_RUN(V_TTS_MISC, tts_logw_kernel<<<gT, 128, 0, st>>>(za, lens, P + L.ea, nullptr, T, 1, 1, ws + W.lws));
   // ---- durations (models.py:474-481)
   long long* ylen = reinterpret_cast<long long*>(ws + W.ylen);
   int* cum = reinterpret_cast<int*>(ws + W.cum);
-  tts_durations_kernel<<<(B + 63) / 64, 64, 0, st>>>(ws + W.lws, ws + W.lwd, lens, sdp_ratio, length_scale, B, T, ws + W.logw,
-                                                     ws + W.wceil, cum, ylen);
-  TTS_LAUNCHED();
-#undef TTS_LAUNCHED
+  TTS_RUN(V_TTS_MISC, tts_durations_kernel<<<(B + 63) / 64, 64, 0, st>>>(ws + W.lws, ws + W.lwd, lens, sdp_ratio, length_scale, B, T, ws + W.logw,
+                                                     ws + W.wceil, cum, ylen));
+#undef TTS_RUN
   if (c->debug) {
     Run r1{c, st, B, T, T, lens, lens, 0.0};
     TRY(tap(r1, "tts.logw_sdp", ws + W.lws, 1, T, T));

@@ -77,6 +77,37 @@ __global__ void tts_dense_kernel(const float* x, const long long* lens, const fl
   out[((size_t)b * T + t) * N + n] = ovc_tts::dense_at(x + (size_t)b * T * Cin, w, bias, Cin, K, N, t, n, len, relu_in);
 }
 
+// channels-last rows -> the [C][P] layout of the FFMA2 conv kernels (ovc_conv.cuh) and back; P = T rounded up to 4.
+// grid (ceil(P/32), ceil(C/32), B), block (32, 8): 32x32 tiles through shared memory, both sides coalesced
+__global__ void tts_to_ct_kernel(const float* x, const long long* lens, int T, int C, int P, float* out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int len = tts_len(lens, b, T);
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < len && c < C) ? x[((size_t)b * T + t) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < P) out[((size_t)b * C + c) * P + t] = tile[threadIdx.x][i];
+  }
+}
+__global__ void tts_from_ct_kernel(const float* in, const long long* lens, int T, int C, int P, float* out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int len = tts_len(lens, b, T);
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < len) ? in[((size_t)b * C + c) * P + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < len && c < C) out[((size_t)b * T + t) * C + c] = tile[threadIdx.x][i];
+  }
+}
+
 // grid (ceil(T*C/256), B)
 __global__ void tts_dwconv_kernel(const float* x, const long long* lens, const float* w, const float* bias, int T, int C,
                                   int dil, float* out) {

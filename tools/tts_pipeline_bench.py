@@ -102,6 +102,11 @@ def main():
     torch.cuda.synchronize()
     enc_wall_ms = (time.perf_counter() - t0) * 1e3
     enc_launches = tts.native.last_launch_count
+    by_kernel = {}
+    for name, ms, fl, by, fam in tts.native.profile_detail():
+        e = by_kernel.setdefault(name, [0, 0.0])
+        e[0] += 1
+        e[1] += ms
     tts.native.profile_enable(False)
 
     res = {
@@ -113,10 +118,12 @@ def main():
         "convert_audio_s_per_s": round(audio_s / conv_ms * 1e3, 1),
         "pipeline_audio_s_per_s": round(audio_s2 / e2e_ms * 1e3, 1),
         "text_front_wall_ms": round(enc_wall_ms, 2), "text_front_launches": enc_launches,
+        "text_front_kernels_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][1])},
         "frames": [int(v) for v in yl.cpu()],
     }
     if a.cpu:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        from bench import host_cores
+        torch.set_num_threads(host_cores())
         n = int(lengths[0])
         with torch.no_grad():
             t0 = time.perf_counter()
