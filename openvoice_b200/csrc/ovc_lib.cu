@@ -1377,6 +1377,10 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
   c->launches = 0;
   const int H = L.H, G = c->hp.gin_channels;
   const dim3 gE((T * H + 255) / 256, B), gRow((T + 63) / 64, B);
+  // OVC_TTS_SIMPLE=1: the one-thread-per-element reference kernels (CPU-checked element functions) instead of the
+  // warp-cooperative LayerNorm / fused attention; also the fallback when the logits of 8 queries exceed 48 KB of smem
+  static const bool simple = getenv("OVC_TTS_SIMPLE") && atoi(getenv("OVC_TTS_SIMPLE")) != 0;
+  const size_t att_smem = sizeof(float) * ((size_t)TTS_ATT_Q * T + (size_t)TTS_ATT_Q * (H / L.heads));
   TcExtra tx; tx.use_lens_frames = true;
   auto dense = [&](const TcLayer& lay, const float* x, float* y, float slope) -> int {
     return launch_tc(r, lay, x, y, nullptr, T, 1, slope, 1.f, 0, 0, tx);
@@ -1423,7 +1427,8 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
   auto ln = [&](const float* a, const float* rr, const float* res, size_t g_off, size_t b_off, int C, int pre, int post,
                 float* out) -> int {
     TRY(prof_begin(r));
-    tts_ln_kernel<<<gRow, 64, 0, st>>>(a, rr, res, P + g_off, P + b_off, lens, T, C, pre, post, out);
+    if (simple) tts_ln_kernel<<<gRow, 64, 0, st>>>(a, rr, res, P + g_off, P + b_off, lens, T, C, pre, post, out);
+    else tts_ln_warp_kernel<<<dim3((T + 3) / 4, B), 128, 0, st>>>(a, rr, res, P + g_off, P + b_off, lens, T, C, pre, post, out);
     CK(cudaGetLastError());
     c->launches++;
     return prof_end(r, V_TTS_LN, 0, 0.0, 0.0);
@@ -1444,8 +1449,13 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
   for (int i = 0; i < L.n_layers; ++i) {
     // MultiHeadAttention (attentions.py:262-324): QKV projection and output projection on the tensor cores
     TRY(dense(L.qkv[i], X, QKV, 1.f));
-    TTS_RUN(V_TTS_SCORES, tts_scores_kernel<<<dim3((T * T + 255) / 256, L.heads, B), 256, 0, st>>>(QKV, lens, P + L.relk[i], T, H, L.heads, L.window, S));
-    TTS_RUN(V_TTS_ATTN, tts_attn_out_kernel<<<gE, 256, 0, st>>>(S, QKV, lens, P + L.relv[i], T, H, L.heads, L.window, A));
+    if (simple || att_smem > 48 * 1024 || (H / L.heads) % 4 != 0) {
+      TTS_RUN(V_TTS_SCORES, tts_scores_kernel<<<dim3((T * T + 255) / 256, L.heads, B), 256, 0, st>>>(QKV, lens, P + L.relk[i], T, H, L.heads, L.window, S));
+      TTS_RUN(V_TTS_ATTN, tts_attn_out_kernel<<<gE, 256, 0, st>>>(S, QKV, lens, P + L.relv[i], T, H, L.heads, L.window, A));
+    } else {
+      TTS_RUN(V_TTS_ATTN, tts_attention_kernel<<<dim3((T + TTS_ATT_Q - 1) / TTS_ATT_Q, L.heads, B), 128, att_smem, st>>>(
+                              QKV, lens, P + L.relk[i], P + L.relv[i], T, H, L.heads, L.window, A));
+    }
     TRY(dense(L.o[i], A, Y, 1.f));
     TRY(ln(X, Y, nullptr, L.ln1g[i], L.ln1b[i], H, 0, 0, X));                  // attentions.py:115
     // FFN (attentions.py:439-448): conv k, relu (as the next conv's input activation), conv k -- fp32 CUDA cores

@@ -41,6 +41,124 @@ __global__ void tts_ln_kernel(const float* a, const float* r, const float* res, 
   ovc_tts::layer_norm_row(a + o, r ? r + o : nullptr, res ? res + o : nullptr, gamma, beta, C, pre, post, out + o);
 }
 
+// Warp-per-row LayerNorm (same math as ovc_tts::layer_norm_row; lanes stride over channels, coalesced, shuffle
+// reductions).  grid (ceil(T/4), B), 128 threads = 4 rows.  In-place safe (a == out, res == out).
+__global__ void tts_ln_warp_kernel(const float* a, const float* r, const float* res, const float* gamma, const float* beta,
+                                   const long long* lens, int T, int C, int pre, int post, float* out) {
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y, lane = threadIdx.x & 31;
+  if (t >= tts_len(lens, b, T)) return;
+  const size_t o = ((size_t)b * T + t) * C;
+  auto val = [&](int c) {
+    float v = a[o + c] + (r ? r[o + c] : 0.f);
+    if (pre == 1) v = v > 0.f ? v : 0.f;
+    return v;
+  };
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += val(c);
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = val(c) - mean; sq += d * d; }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, m);
+  const float rstd = 1.f / sqrtf(sq / (float)C + 1e-5f);
+  for (int c = lane; c < C; c += 32) {
+    float y = (val(c) - mean) * rstd * gamma[c] + beta[c];
+    if (post == 1) y = ovc_tts::gelu_erf(y);
+    out[o + c] = y + (res ? res[o + c] : 0.f);
+  }
+}
+
+// Fused relative-position self-attention (attentions.py:272-324), same math as ovc_tts::attn_score / attn_out:
+// one CTA = 8 queries of one (utterance, head); logits and probabilities live in shared memory.
+// grid (ceil(T/8), heads, B), 128 threads, dynamic smem = (8 * T + 8 * dk) floats.  dk % 4 == 0.
+constexpr int TTS_ATT_Q = 8;
+__global__ void tts_attention_kernel(const float* qkv, const long long* lens, const float* rel_k, const float* rel_v, int T,
+                                     int H, int heads, int window, float* out) {
+  extern __shared__ float att_smem[];
+  const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TTS_ATT_Q;
+  const int len = tts_len(lens, b, T);
+  if (i0 >= len) return;
+  const int dk = H / heads, ld = 3 * H, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sq = att_smem;                    // [8][dk]   queries, pre-scaled by 1/sqrt(dk)
+  float* sp = att_smem + TTS_ATT_Q * dk;   // [8][T]    logits, then probabilities
+  const float* base = qkv + (size_t)b * T * ld;
+  const float inv = 1.f / sqrtf((float)dk);
+  const int nq = min(TTS_ATT_Q, len - i0);
+  for (int e = tid; e < TTS_ATT_Q * dk; e += blockDim.x) {
+    const int qi = e / dk, d = e % dk;
+    sq[e] = qi < nq ? base[(size_t)(i0 + qi) * ld + h * dk + d] * inv : 0.f;
+  }
+  __syncthreads();
+  // logits: thread <- key j; the key row streams through registers four channels at a time
+  for (int j = tid; j < len; j += blockDim.x) {
+    const float* kr = base + (size_t)j * ld + H + h * dk;
+    float acc[TTS_ATT_Q];
+#pragma unroll
+    for (int qi = 0; qi < TTS_ATT_Q; ++qi) acc[qi] = 0.f;
+    for (int d = 0; d < dk; d += 4) {
+      const float4 kv = *reinterpret_cast<const float4*>(kr + d);
+#pragma unroll
+      for (int qi = 0; qi < TTS_ATT_Q; ++qi) {
+        const float* q = sq + qi * dk + d;
+        acc[qi] += q[0] * kv.x + q[1] * kv.y + q[2] * kv.z + q[3] * kv.w;
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < TTS_ATT_Q; ++qi) {
+      const int rel = j - (i0 + qi);
+      float s = acc[qi];
+      if (qi < nq && rel >= -window && rel <= window) {                 // relative-key logits (attentions.py:282-291)
+        const float* e = rel_k + (size_t)(rel + window) * dk;
+        const float* q = sq + qi * dk;
+        float sl = 0.f;
+        for (int d = 0; d < dk; ++d) sl += q[d] * e[d];
+        s += sl;
+      }
+      sp[qi * T + j] = s;
+    }
+  }
+  __syncthreads();
+  // softmax over keys: warp w owns queries 2w, 2w + 1
+  for (int qi = warp * 2; qi < warp * 2 + 2; ++qi) {
+    if (qi >= nq) continue;
+    float* row = sp + qi * T;
+    float m = -3.4e38f;
+    for (int j = lane; j < len; j += 32) m = fmaxf(m, row[j]);
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    float den = 0.f;
+    for (int j = lane; j < len; j += 32) { const float e = expf(row[j] - m); row[j] = e; den += e; }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) den += __shfl_xor_sync(0xffffffffu, den, k);
+    const float rden = 1.f / den;
+    for (int j = lane; j < len; j += 32) row[j] *= rden;
+  }
+  __syncthreads();
+  // value mix: thread <- channel d (coalesced value rows), 8 queries at once; then the relative-value term
+  for (int d = tid; d < dk; d += blockDim.x) {
+    float acc[TTS_ATT_Q];
+#pragma unroll
+    for (int qi = 0; qi < TTS_ATT_Q; ++qi) acc[qi] = 0.f;
+    const float* vcol = base + 2 * H + h * dk + d;
+    for (int j = 0; j < len; ++j) {
+      const float v = vcol[(size_t)j * ld];
+#pragma unroll
+      for (int qi = 0; qi < TTS_ATT_Q; ++qi) acc[qi] += sp[qi * T + j] * v;
+    }
+    for (int qi = 0; qi < nq; ++qi) {
+      const int i = i0 + qi;
+      float a = acc[qi];
+      for (int rel = -window; rel <= window; ++rel) {
+        const int j = i + rel;
+        if (j >= 0 && j < len) a += sp[qi * T + j] * rel_v[(size_t)(rel + window) * dk + d];
+      }
+      out[((size_t)b * T + i) * H + h * dk + d] = a;
+    }
+  }
+}
+
 // grid (ceil(T*T/256), heads, B): scores [B][heads][T][T]
 __global__ void tts_scores_kernel(const float* qkv, const long long* lens, const float* rel_k, int T, int H, int heads,
                                   int window, float* scores) {

@@ -181,10 +181,10 @@ OVC_HD float rq_spline_inverse(float x, const float* p, float scale, float bound
 // h_row [C]; pw [NP][C], pb [NP]                                               modules.py:488-516
 OVC_HD float convflow_tail(const float* h_row, const float* pw, const float* pb, int C, float x1, float bound) {
   float p[NP];
-  for (int n = 0; n < NP; ++n) {
-    float acc = pb[n];
-    for (int c = 0; c < C; ++c) acc += pw[(size_t)n * C + c] * h_row[c];
-    p[n] = acc;
+  for (int n = 0; n < NP; ++n) p[n] = pb[n];
+  for (int c = 0; c < C; ++c) {            // channel-outer: one read of h per channel, the NP weights are warp-uniform
+    const float hv = h_row[c];
+    for (int n = 0; n < NP; ++n) p[n] += pw[(size_t)n * C + c] * hv;
   }
   return rq_spline_inverse(x1, p, sqrtf((float)C), bound);
 }
