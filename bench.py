@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("OVC_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32"],
                     help="generator conv arithmetic: tf32x3 = split-precision tensor cores (default, fp32-grade), "
                          "fp32 = CUDA-core FFMA2, tf32 = single-pass TF32 (the reference's own GPU default)")
+    ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE config-3 side measurement (V1 TTS + convert, batch 16)")
     ap.add_argument("--no-modes", action="store_true", help="skip the short side measurements of the other precisions")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -403,6 +404,19 @@ def main():
         v, dt, threads, done = cpu_reference_throughput(args.cpu_clips, secs)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
                                 "sample": f"{done} x {secs:g} s clips, batch 1 each (convert semantics), fp32 torch CPU, {dt:.1f} s"}
+    if world == 1 and not args.no_config3:
+        # BASELINE.json configs[2] (V1 BaseSpeakerTTS.tts + convert, batch 16): a side measurement, never the headline
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location(
+                "tts_pipeline_bench", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "tts_pipeline_bench.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            r3 = mod.measure(batch=16, tokens=121, iters=3, cpu=False, precision=args.precision)
+            line["config3"] = {k: r3[k] for k in ("workload", "audio_s_per_batch", "tts_ms", "convert_ms", "e2e_ms",
+                                                  "tts_audio_s_per_s", "pipeline_audio_s_per_s", "text_front_launches")}
+        except Exception as e:      # a side measurement must never cost the headline line
+            line["config3"] = {"error": f"{type(e).__name__}: {e}"[:240]}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

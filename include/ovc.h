@@ -155,15 +155,16 @@ OVC_API int ovc_reference_encoder(ovc_ctx* ctx, const float* spec, int N, int T,
  *
  * tokens [B][T] int64 (padded), x_lengths [B] int64, sid [B] int64, noise_w [B][2][T] or NULL (Philox from `seed`);
  * y_lengths [B] int64 out; w_ceil / logw [B][T] optional outs.  All device pointers.  ovc_tts_decode uses the state the
- * last ovc_tts_encode left in the context: noise [B][inter][Ymax] or NULL (Philox), Ymax >= max(y_lengths) (a smaller
- * value is the reference's max_len), ragged as in ovc_voice_conversion; o [B][Ymax*hop], z / z_p [B][inter][Ymax]
- * optional.  ovc_tts_info: out8 = {has_tts, n_vocab, n_speakers, n_heads, n_layers, window, filter_channels, dp_filter}. */
+ * last ovc_tts_encode left in the context: noise [B][inter][Ymax] or NULL (Philox), Ymax = max(y_lengths) (the
+ * caller reads y_lengths back, as the reference does), max_len = the reference's max_len (0: none; the flow still runs
+ * on all Ymax frames, only the generator is cut, models.py:489), ragged as in ovc_voice_conversion;
+ * o [B][min(Ymax, max_len)*hop], z / z_p [B][inter][Ymax] optional.  ovc_tts_info: out8 = {has_tts, n_vocab, n_speakers, n_heads, n_layers, window, filter_channels, dp_filter}. */
 OVC_API int ovc_tts_info(const ovc_ctx* ctx, int32_t* out8);
 OVC_API int ovc_tts_encode(ovc_ctx* ctx, const int64_t* tokens, const int64_t* x_lengths, const int64_t* sid,
                            const float* noise_w, uint64_t seed, float noise_scale_w, float length_scale, float sdp_ratio,
                            int B, int T, int64_t* y_lengths, float* w_ceil, float* logw, void* stream);
-OVC_API int ovc_tts_decode(ovc_ctx* ctx, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int ragged,
-                           float* o, float* z, float* z_p, void* stream);
+OVC_API int ovc_tts_decode(ovc_ctx* ctx, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int max_len,
+                           int ragged, float* o, float* z, float* z_p, void* stream);
 
 /* Arithmetic of the generator's ResBlock convolutions (90 % of the FLOPs):
  *   0 (default)  fp32 FFMA2 on the CUDA cores

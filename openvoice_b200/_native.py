@@ -83,8 +83,8 @@ def load_library(path: Optional[str] = None):
     lib.ovc_tts_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     lib.ovc_tts_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float,
                                    C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.ovc_tts_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ovc_tts_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if lib.ovc_abi_version() != ABI_VERSION:
         raise OvcError(f"ABI mismatch: library {lib.ovc_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
@@ -299,19 +299,20 @@ class NativeConverter:
         return y_lengths, w_ceil, logw
 
     def tts_decode(self, B: int, y_max: int, device, noise=None, seed: int = 0, noise_scale: float = 1.0,
-                   ragged: bool = False, latents: bool = False, stream=None):
-        """Second half of infer() for the last tts_encode.  Returns (o [B,1,hop*y_max], (z, z_p) or None)."""
+                   ragged: bool = False, latents: bool = False, max_len: Optional[int] = None, stream=None):
+        """Second half of infer() for the last tts_encode.  Returns (o [B,1,hop*min(y_max, max_len)], (z, z_p) or None)."""
         import torch
         C_ = self.hp.inter_channels
         if noise is not None:
             noise = noise.contiguous().float()
             assert noise.is_cuda and tuple(noise.shape) == (B, C_, y_max)
-        o = torch.empty(B, 1, self.hp.hop_length * y_max, device=device, dtype=torch.float32)
+        cut = int(max_len) if max_len is not None and 0 < int(max_len) < y_max else 0
+        o = torch.empty(B, 1, self.hp.hop_length * (cut or y_max), device=device, dtype=torch.float32)
         lat = tuple(torch.empty(B, C_, y_max, device=device, dtype=torch.float32) for _ in range(2)) if latents else None
         st = stream if stream is not None else torch.cuda.current_stream(device)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
         rc = self.lib.ovc_tts_decode(self.handle, p(noise), C.c_uint64(seed & (2 ** 64 - 1)), C.c_float(noise_scale), B,
-                                     int(y_max), 1 if ragged else 0, p(o), p(lat[0]) if lat else None,
+                                     int(y_max), cut, 1 if ragged else 0, p(o), p(lat[0]) if lat else None,
                                      p(lat[1]) if lat else None, C.c_void_p(st.cuda_stream))
         _check(self.lib, rc, "ovc_tts_decode")
         return o, lat

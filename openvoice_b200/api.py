@@ -174,12 +174,10 @@ class NativeSynthesizer:
                                                       noise_scale_w=float(noise_scale_w), length_scale=float(length_scale),
                                                       sdp_ratio=float(sdp_ratio))
         Ty = int(y_lengths.max().item())                       # the sync
-        if max_len is not None:
-            Ty = min(Ty, int(max_len))
         if noise is not None:
             noise = noise.to(self.device, torch.float32)[:, :, :Ty].contiguous()
         o, lat = self.native.tts_decode(B, Ty, self.device, noise=noise, seed=seed + 1, noise_scale=float(noise_scale),
-                                        ragged=ragged, latents=latents)
+                                        ragged=ragged, latents=latents, max_len=max_len)
         ar = torch.arange(Ty, device=self.device)
         y_mask = (ar[None, :] < y_lengths[:, None]).unsqueeze(1).to(torch.float32)
         cum = torch.cumsum(w_ceil, 1)                          # commons.generate_path (commons.py:128-142)

@@ -1535,8 +1535,8 @@ static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* 
 }
 
 // durations -> waveform: expand m_p / logs_p along the path, sample z_p, flow reverse, generator (models.py:482-490)
-static int run_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int ragged,
-                          float* o, float* z_out, float* zp_out, cudaStream_t st) {
+static int run_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int max_len,
+                          int ragged, float* o, float* z_out, float* zp_out, cudaStream_t st) {
   const TtsLayers& L = c->tts;
   const int T = c->tts_T;
   const TtsWs TW = tts_ws_layout(c, B, T);
@@ -1568,7 +1568,10 @@ static int run_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float n
   const float* cond = ws + W.cond;
   TRY(run_flow(r, W, ws, true, cond));
   TRY(copy_latent_out(r, W, ws, z_out));
-  return run_dec(r, W, ws, cond, ylen, o);
+  // o = dec((z * y_mask)[:, :, :max_len]) (models.py:489): the flow above saw every frame, only the generator is cut
+  Run rd = r;
+  if (max_len > 0 && max_len < Ymax) rd.Tmax = max_len;
+  return run_dec(rd, W, ws, cond, ylen, o);
 }
 
 }  // namespace ovc
@@ -1786,8 +1789,8 @@ int ovc_tts_encode(ovc_ctx* c, const int64_t* tokens, const int64_t* x_lengths, 
                         noise_scale_w, length_scale, sdp_ratio, B, T, (long long*)y_lengths, w_ceil, logw, (cudaStream_t)stream);
 }
 
-int ovc_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int ragged, float* o,
-                   float* z, float* z_p, void* stream) {
+int ovc_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int max_len, int ragged,
+                   float* o, float* z, float* z_p, void* stream) {
   if (!c) return fail(OVC_ERR_INVALID, "null context");
   if (!c->finalized || !c->tts.ready) return fail(OVC_ERR_STATE, "no finalized TTS checkpoint");
   if (c->tts_B < 1) return fail(OVC_ERR_STATE, "ovc_tts_decode needs a preceding ovc_tts_encode");
@@ -1797,7 +1800,8 @@ int ovc_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_sc
   if ((long long)Ymax * 256 * 64 > 2000000000LL) return fail(OVC_ERR_INVALID, "Ymax %d too large for 32-bit indexing", Ymax);
   CK(cudaSetDevice(c->device));
   c->ev_used = c->prof ? c->ev_used : 0;
-  return run_tts_decode(c, noise, seed, noise_scale, B, Ymax, ragged, o, z, z_p, (cudaStream_t)stream);
+  if (max_len < 0) return fail(OVC_ERR_INVALID, "max_len must be >= 0 (0 = no limit)");
+  return run_tts_decode(c, noise, seed, noise_scale, B, Ymax, max_len, ragged, o, z, z_p, (cudaStream_t)stream);
 }
 
 int ovc_set_precision(ovc_ctx* c, int mode) {

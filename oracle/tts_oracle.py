@@ -377,7 +377,8 @@ def generate_path(w_ceil: torch.Tensor, y_lengths: torch.Tensor) -> torch.Tensor
 def tts_infer(sd: StateDict, tokens: torch.Tensor, lengths: torch.Tensor, sid: torch.Tensor,
               noise_w: torch.Tensor, noise: Optional[torch.Tensor] = None, noise_scale: float = 0.667,
               length_scale: float = 1.0, noise_scale_w: float = 0.6, sdp_ratio: float = 0.2,
-              hp: Optional[dict] = None, tts: Optional[dict] = None, ragged: bool = False) -> dict:
+              hp: Optional[dict] = None, tts: Optional[dict] = None, ragged: bool = False,
+              max_len: Optional[int] = None) -> dict:
     """SynthesizerTrn.infer (models.py:467-490).  ``noise`` [B,C,Ty] replaces torch.randn_like at :487
     (None -> zeros).  ``ragged``: decode every utterance on its own length (what a B=1 call gives)."""
     hp = hp or V.DEFAULT_HPARAMS
@@ -414,5 +415,5 @@ def tts_infer(sd: StateDict, tokens: torch.Tensor, lengths: torch.Tensor, sid: t
     else:
         z = V.flow(sd, z_p, y_mask, g, reverse=True)
         res["z"] = z
-        res["o"] = V.generator(sd, z * y_mask, g, hp)
+        res["o"] = V.generator(sd, (z * y_mask)[:, :, :max_len], g, hp)          # models.py:489
     return res

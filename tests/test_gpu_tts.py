@@ -194,3 +194,66 @@ def test_simple_kernels_fallback_matches_reference():
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert "SIMPLE_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_max_len_cuts_the_generator_only(tts):
+    """o = dec((z * y_mask)[:, :, :max_len]) (models.py:489): the flow runs on every frame, the generator on the first max_len."""
+    from oracle import tts_oracle as T
+    d, c = load("tts_b1_t37")
+    tokens, lengths, sid, noise_w, noise = inputs(c)
+    kw = dict(noise_scale=c["noise_scale"], length_scale=c["length_scale"], noise_scale_w=c["noise_scale_w"],
+              sdp_ratio=c["sdp_ratio"])
+    o, _, y_mask, (z, _, _, _) = tts.infer(tokens, lengths, sid=sid, noise_w=noise_w, noise=noise, max_len=40, **kw)
+    torch.cuda.synchronize()
+    assert tuple(o.shape) == (1, 1, 40 * 256) and y_mask.shape[-1] == int(d["y_lengths"][0])
+    with torch.no_grad():
+        r = T.tts_infer(T.synthetic_tts_state_dict(), tokens, lengths, sid, noise_w, noise, max_len=40, **kw)
+    ref = r["o"].numpy()
+    assert np.abs(o.cpu().numpy() - ref).max() < 1e-4 * rms(ref)
+    assert np.abs(z.cpu().numpy() - d["z"]).max() < 1e-4 * rms(d["z"])        # z is the full-length latent
+
+
+def test_one_token_and_very_long_text(tts):
+    """T = 1 (every conv is all padding) and T = 1500 (8 x T logits exceed 48 KB: the plain attention kernels take over)."""
+    from oracle import tts_oracle as T
+    from oracle import vc_oracle as V
+    sd = T.synthetic_tts_state_dict()
+    for B, Tn, lens in ((1, 1, [1]), (2, 1500, [1500, 700])):
+        tokens, lengths, sid, noise_w = T.synthetic_tts_inputs(B, Tn, 21, lens)
+        dev = tts.device
+        yl, w_ceil, logw = tts.native.tts_encode(tokens.to(dev), lengths.to(dev), sid.to(dev), noise_w=noise_w.to(dev),
+                                                 noise_scale_w=0.6, length_scale=1.0, sdp_ratio=0.2)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            x, _, _, mask = T.text_encoder(sd, tokens, lengths)
+            g = sd["emb_g.weight"][sid].unsqueeze(-1)
+            lw = T.sdp_reverse(sd, x, mask, g, noise_w, 0.6) * 0.2 + T.duration_predictor(sd, x, mask, g) * 0.8
+            ref = torch.ceil(torch.exp(lw) * mask)[:, 0].numpy()
+        got = w_ceil.cpu().numpy()
+        assert np.abs(logw.cpu().numpy() - (lw * mask)[:, 0].numpy()).max() < 5e-4
+        diff = np.abs(got - ref)
+        assert diff.max() <= 1 and (diff > 0).sum() <= max(1, int(0.002 * ref.size)), (B, Tn, int((diff > 0).sum()))
+        if Tn == 1:
+            o, _, y_mask, _ = tts.infer(tokens, lengths, sid=sid, noise_w=noise_w, noise_scale=0.5, noise_scale_w=0.6, seed=1)
+            torch.cuda.synchronize()
+            assert o.shape[-1] == int(got.sum()) * 256 and torch.isfinite(o).all()
+
+
+def test_decode_needs_a_matching_encode(tts):
+    from oracle import tts_oracle as T
+    from openvoice_b200._native import OvcError
+    from conftest import get_native
+    conv = get_native(False)                                      # converter checkpoint: no TTS members
+    assert conv.native.tts_info()["has_tts"] == 0
+    with pytest.raises(OvcError):
+        conv.native.tts_decode(1, 10, conv.device)
+    with pytest.raises(RuntimeError):
+        conv.infer(torch.zeros(1, 3, dtype=torch.int64), torch.tensor([3]), sid=torch.tensor([0]))
+    tokens, lengths, sid, noise_w = T.synthetic_tts_inputs(2, 9, 5)
+    dev = tts.device
+    tts.native.tts_encode(tokens.to(dev), lengths.to(dev), sid.to(dev), noise_w=noise_w.to(dev))
+    with pytest.raises(ValueError):
+        tts.native.tts_decode(3, 40, dev)                         # B differs from the pending encode
+    o, _ = tts.native.tts_decode(2, 40, dev, seed=3, noise_scale=0.3)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o).all()

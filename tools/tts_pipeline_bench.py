@@ -23,14 +23,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--tokens", type=int, default=121)
-    ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on one sentence (test infrastructure)")
-    ap.add_argument("--precision", default="tf32x3")
-    a = ap.parse_args()
+def measure(batch=16, tokens=121, iters=5, cpu=False, precision="tf32x3"):
+    a = argparse.Namespace(batch=batch, tokens=tokens, iters=iters, cpu=cpu, precision=precision)
 
     from oracle import tts_oracle as T          # synthetic checkpoint recipe + the optional CPU leg only
     from oracle import vc_oracle as V
@@ -132,7 +126,18 @@ def main():
             t_tts = time.perf_counter() - t0
         secs = int(r["y_lengths"][0]) * hop / 22050.0
         res["cpu_port_tts"] = {"audio_s_per_s": round(secs / t_tts, 2), "sample": "1 sentence", "threads": torch.get_num_threads()}
-    print(json.dumps(res))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--tokens", type=int, default=121)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on one sentence (test infrastructure)")
+    ap.add_argument("--precision", default="tf32x3")
+    a = ap.parse_args()
+    print(json.dumps(measure(a.batch, a.tokens, a.iters, a.cpu, a.precision)))
 
 
 if __name__ == "__main__":
