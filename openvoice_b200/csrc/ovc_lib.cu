@@ -444,7 +444,7 @@ static int pack_tts(ovc_ctx* c) {
         for (int tap = 0; tap < k; ++tap) t.data[((size_t)tap * cin + ci) * cout + n] = w->data[((size_t)n * cin + ci) * k + tap];
     d.w = put(&t); d.b = put(b); d.Cin = cin; d.K = k; d.N = cout;
     if (k == 3 && cout % 64 == 0 && cin % 8 == 0) {
-      d.cl = pack_conv(c, cout % 128 == 0 ? V_A_K3D1 : V_B_K3D1, cout, cin,
+      d.cl = pack_conv(c, cout % 128 == 0 ? V_A_K3D1 : V_TXT_K3D1, cout, cin,
                        [&](int r, int ci, int tap) { return w->data[((size_t)r * cin + ci) * k + tap]; },
                        [&](int r) { return b->data[r]; }, cout, k, cout);
       d.fast = true;

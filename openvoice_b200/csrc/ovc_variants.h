@@ -14,7 +14,8 @@
   X(FLOW_POST, 1, 1, 1, 4, 8, EPI_COUPLE, 1, 16)            \
   X(UPS8_A, 3, 1, 4, 2, 8, EPI_UPS8, 1, 16)                 \
   X(UPS2_A, 3, 1, 4, 2, 8, EPI_UPS2, 1, 16)                 \
-  X(UPS2_B, 3, 1, 2, 4, 8, EPI_UPS2, 1, 16)
+  X(UPS2_B, 3, 1, 2, 4, 8, EPI_UPS2, 1, 16)                 \
+  X(TXT_K3D1, 3, 1, 2, 2, 8, EPI_LINEAR, 1, 16)   /* TTS text side: k = 3 convs on short sequences (64 x 128 tiles) */
 
 // generator, class A: 128 rows x 128 samples (C = 512, 256, 128)
 #define OVC_VARIANTS_G1(X)                                  \
