@@ -230,7 +230,9 @@ def test_one_token_and_very_long_text(tts):
             lw = T.sdp_reverse(sd, x, mask, g, noise_w, 0.6) * 0.2 + T.duration_predictor(sd, x, mask, g) * 0.8
             ref = torch.ceil(torch.exp(lw) * mask)[:, 0].numpy()
         got = w_ceil.cpu().numpy()
-        assert np.abs(logw.cpu().numpy() - (lw * mask)[:, 0].numpy()).max() < 5e-4
+        e_logw = np.abs(logw.cpu().numpy() - (lw * mask)[:, 0].numpy())
+        print("long text", (B, Tn), "logw err max", float(e_logw.max()), "n > 5e-4:", int((e_logw > 5e-4).sum()))
+        assert e_logw.max() < 5e-4, (B, Tn, float(e_logw.max()), int((e_logw > 5e-4).sum()))
         diff = np.abs(got - ref)
         assert diff.max() <= 1 and (diff > 0).sum() <= max(1, int(0.002 * ref.size)), (B, Tn, int((diff > 0).sum()))
         if Tn == 1:
