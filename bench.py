@@ -371,10 +371,19 @@ def main():
         # costs 3 tensor FLOPs in the split-precision mode.
         passes = 3 if args.precision == "tf32x3" else 1
         tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        tc_traffic, tc_note = None, None
+        try:   # dram bytes of a representative launch of this kernel from the committed ncu --set full capture
+            caps = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_tcconv128_mrf_c256_c128_before_issue_fix.json")))
+            cap = [c for c in caps if c.get("launch__grid_size") == "1728"][1]
+            tc_traffic = (float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])) * 1e6
+            tc_note = ("ncu dram read+write of ONE tcconv_kernel<128> launch (C=128 ResBlock conv, batch 8 x 861 frames, "
+                       "55104 steps): algorithmic in + out = 451 MB; per-launch figure at another batch size, not this step's")
+        except Exception:
+            pass
         roofline = {
             "kernel": "tcconv_kernel<TN> (generator ResBlock1 convs on tcgen05, 72 launches per call)",
             "bound": "tensor", "achieved": ach_tf * passes, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": ach_tf * passes / tf32_peak, "traffic": None,
+            "frac": ach_tf * passes / tf32_peak, "traffic": tc_traffic, "traffic_note": tc_note,
             "peak_source": ("measured" if "bf16_tflops_sustained" in peaks else "fallback") + " bf16 sustained / 2 (TF32 rate)",
             "algorithmic_tflops": ach_tf, "mma_passes": passes,
             "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_dev,
