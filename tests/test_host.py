@@ -207,3 +207,27 @@ def test_multi_gpu_driver_under_gloo_world2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "worker-0-ok" in r.stdout and "worker-1-ok" in r.stdout
+
+
+def test_tts_key_schema_matches_the_oracle_schema(hps):
+    """openvoice_b200.schema.tts_keys (what load_state_dict reports against) = the reference constructors' names as the
+    oracle lists them, minus sdp.flows.1 (never run in reverse, models.py:172)."""
+    from oracle import tts_oracle as T
+    from openvoice_b200.schema import hot_path_keys, tts_keys
+    want = {k for k in T.tts_state_dict_schema() if not k.startswith("sdp.flows.1.")}
+    assert set(tts_keys(hps)) == want
+    sd = T.synthetic_tts_state_dict()
+    assert set(hot_path_keys(hps)) | set(tts_keys(hps)) <= set(sd)
+
+
+def test_base_speaker_host_helpers():
+    """commons.intersperse (commons.py:22-25) and BaseSpeakerTTS.audio_numpy_concat (api.py:56-63)."""
+    import numpy as np
+    from openvoice_b200.api import BaseSpeakerTTS
+    assert BaseSpeakerTTS.intersperse([5, 6, 7], 0) == [0, 5, 0, 6, 0, 7, 0]
+    assert BaseSpeakerTTS.intersperse([], 0) == [0]
+    a = BaseSpeakerTTS.audio_numpy_concat([np.ones(10), np.full((1, 4), 2.0)], sr=1000, speed=2.0)
+    gap = int(1000 * 0.05 / 2.0)
+    assert a.dtype == np.float32 and len(a) == 10 + 4 + 2 * gap
+    assert a[:10].tolist() == [1.0] * 10 and a[10:10 + gap].tolist() == [0.0] * gap and a[10 + gap:14 + gap].tolist() == [2.0] * 4
+    assert BaseSpeakerTTS.language_marks == {"english": "EN", "chinese": "ZH"}
