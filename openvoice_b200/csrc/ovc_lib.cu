@@ -16,6 +16,12 @@
 #include "../../include/ovc.h"
 #include "ovc_small.cuh"
 #include "ovc_tcconv.cuh"
+#ifndef OVC_TC_PAIR
+#define OVC_TC_PAIR 0   // 1: wide layers on CTA pairs (ovc_tcconv_pair.cuh) -- experimental, not in the default build
+#endif
+#if OVC_TC_PAIR
+#include "ovc_tcconv_pair.cuh"
+#endif
 #include "ovc_tts.cuh"
 #include "ovc_refenc.cuh"
 #include "ovc_variants.h"
@@ -364,6 +370,14 @@ static TcLayer pack_tc(ovc_ctx* c, int Ntot, int Cin, int K, int DIL, WF wfun, B
               bits &= 0xFFFFE000u;
               float hi;
               memcpy(&hi, &bits, 4);
+#if OVC_TC_PAIR
+              if (T.TN == 128) {   // pair layout: [rank][hi|lo][k chunk][64][4], CTA `rank` stages columns [64 * rank, +64)
+                const int rank = n / 64, nn = n % 64;
+                sl[(((rank * 2 + 0) * 2 + kc) * 64 + nn) * 4 + e] = hi;
+                sl[(((rank * 2 + 1) * 2 + kc) * 64 + nn) * 4 + e] = w - hi;
+                continue;
+              }
+#endif
               sl[(kc * T.TN + n) * 4 + e] = hi;
               sl[2 * T.TN * 4 + (kc * T.TN + n) * 4 + e] = w - hi;
             }
@@ -775,6 +789,9 @@ static int finalize(ovc_ctx* c) {
   c->h_tcw.clear();
   c->h_tcw.shrink_to_fit();
   CK(cudaFuncSetAttribute(tcconv_kernel<128, TC_CL128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<128>::SMEM_BYTES));
+#if OVC_TC_PAIR
+  CK(cudaFuncSetAttribute(tcconv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPairCfg::SMEM_BYTES));
+#endif
   CK(cudaFuncSetAttribute(tcconv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<64>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tcconv_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<32>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tcconv_narrow_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<64>::SMEM_BYTES));
@@ -975,6 +992,12 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   const int steps = (T.TN == 128 ? TcCfg<128>::MT : TcCfg<64>::MT) * 128;
   dim3 grid((t_len + steps - 1) / steps, T.Ntot / T.TN, r.B);
   TRY(prof_begin(r));
+#if OVC_TC_PAIR
+  if (T.TN == 128) {
+    grid.x = (grid.x + 1) / 2 * 2;                             // whole CTA pairs along time
+    tcconv_pair_kernel<<<grid, TC_THREADS, TcPairCfg::SMEM_BYTES, r.st>>>(a);
+  } else
+#endif
   if (T.TN == 128) {
     grid.x = (grid.x + TC_CL128 - 1) / TC_CL128 * TC_CL128;   // whole clusters along time
     cudaLaunchConfig_t cfg{};
