@@ -410,152 +410,7 @@ static int pack_wn_tc(ovc_ctx* c, const std::string& prefix, int n_layers, WNLay
   return 0;
 }
 
-// ---- V1 TTS front half: TextEncoder (models.py:16-57, attentions.py:37-121), DurationPredictor (models.py:60-100),
-// StochasticDurationPredictor reverse path (models.py:102-143), emb_g (models.py:465).  Every hyper-parameter is read
-// off the tensor shapes.
-static int pack_tts(ovc_ctx* c) {
-  TtsLayers& L = c->tts;
-  const ovc_hparams& hp = c->hp;
-  std::string err;
-  auto get = [&](const std::string& k, std::initializer_list<int64_t> shape) -> const HostTensor* {
-    const HostTensor* t = find(c, k);
-    if (!t) { if (err.empty()) err = "checkpoint tensor '" + k + "' is missing"; return nullptr; }
-    if (shape.size()) {
-      bool ok = t->shape.size() == shape.size();
-      size_t i = 0;
-      for (int64_t d : shape) { if (ok && d >= 0 && t->shape[i] != d) ok = false; ++i; }
-      if (!ok) { if (err.empty()) err = "checkpoint tensor '" + k + "' has the wrong shape"; return nullptr; }
-    }
-    return t;
-  };
-  auto put = [&](const HostTensor* t) -> size_t {
-    if (!t) return 0;
-    const size_t o = round_up(c->h_w.size(), 64);
-    c->h_w.resize(o + t->data.size());
-    std::copy(t->data.begin(), t->data.end(), c->h_w.begin() + o);
-    return o;
-  };
-  // dense conv [Cout][Cin][K] -> tensor-core layer
-  auto dense = [&](const std::string& prefix, int cout, int cin, int k) -> TcLayer {
-    const HostTensor* w = get(prefix + ".weight", {cout, cin, k});
-    const HostTensor* b = get(prefix + ".bias", {cout});
-    if (!w || !b) return TcLayer();
-    return pack_tc(c, cout, cin, k, 1, [&](int n, int ci, int tap) { return w->data[((size_t)n * cin + ci) * k + tap]; },
-                   [&](int n) { return b->data[n]; });
-  };
-
-  // dense conv kept in fp32: transposed to [K][Cin][N] for coalesced weight reads (ovc_tts_ops.h dense_at)
-  auto dense32 = [&](const std::string& prefix, int cout, int cin, int k) -> TtsLayers::Fp32Dense {
-    TtsLayers::Fp32Dense d;
-    const HostTensor* w = get(prefix + ".weight", {cout, cin, k});
-    const HostTensor* b = get(prefix + ".bias", {cout});
-    if (!w || !b) return d;
-    HostTensor t;
-    t.shape = {k, cin, cout};
-    t.data.resize(w->data.size());
-    for (int n = 0; n < cout; ++n)
-      for (int ci = 0; ci < cin; ++ci)
-        for (int tap = 0; tap < k; ++tap) t.data[((size_t)tap * cin + ci) * cout + n] = w->data[((size_t)n * cin + ci) * k + tap];
-    d.w = put(&t); d.b = put(b); d.Cin = cin; d.K = k; d.N = cout;
-    if (k == 3 && cout % 64 == 0 && cin % 8 == 0) {
-      d.cl = pack_conv(c, cout % 128 == 0 ? V_A_K3D1 : V_TXT_K3D1, cout, cin,
-                       [&](int r, int ci, int tap) { return w->data[((size_t)r * cin + ci) * k + tap]; },
-                       [&](int r) { return b->data[r]; }, cout, k, cout);
-      d.fast = true;
-    }
-    return d;
-  };
-
-  const HostTensor* emb = get("enc_p.emb.weight", {-1, -1});
-  if (!emb) return fail(OVC_ERR_MISSING, "%s", err.c_str());
-  L.n_vocab = (int)emb->shape[0];
-  L.H = (int)emb->shape[1];
-  L.C = hp.inter_channels;
-  const int H = L.H, G = hp.gin_channels;
-  if (H != hp.hidden_channels) return fail(OVC_ERR_INVALID, "enc_p.emb.weight has %d channels, hidden_channels is %d", H, hp.hidden_channels);
-  const HostTensor* rk0 = get("enc_p.encoder.attn_layers.0.emb_rel_k", {1, -1, -1});
-  const HostTensor* f10 = get("enc_p.encoder.ffn_layers.0.conv_1.weight", {-1, H, -1});
-  const HostTensor* dp1 = get("dp.conv_1.weight", {-1, H, 3});
-  const HostTensor* eg = get("emb_g.weight", {-1, G});
-  if (!rk0 || !f10 || !dp1 || !eg) return fail(OVC_ERR_MISSING, "%s", err.c_str());
-  const int dk = (int)rk0->shape[2];
-  L.window = ((int)rk0->shape[1] - 1) / 2;
-  L.heads = dk > 0 ? H / dk : 0;
-  L.Fc = (int)f10->shape[0];
-  const int fk = (int)f10->shape[2];
-  L.D = (int)dp1->shape[0];
-  L.n_speakers = (int)eg->shape[0];
-  if (L.heads < 1 || L.heads * dk != H || fk % 2 == 0 || H % 32 || (2 * L.C) % 32)
-    return fail(OVC_ERR_INVALID, "unsupported TTS geometry (H %d, heads %d, filter %d, ffn kernel %d, dp filter %d)", H, L.heads,
-                L.Fc, fk, L.D);
-  while (find(c, "enc_p.encoder.attn_layers." + std::to_string(L.n_layers) + ".conv_q.weight")) ++L.n_layers;
-  if (L.n_layers < 1) return fail(OVC_ERR_MISSING, "enc_p.encoder has no attention layers");
-
-  L.emb = put(emb);
-  L.emb_g = put(eg);
-  for (int i = 0; i < L.n_layers; ++i) {
-    const std::string a = "enc_p.encoder.attn_layers." + std::to_string(i);
-    const HostTensor *wq = get(a + ".conv_q.weight", {H, H, 1}), *wk = get(a + ".conv_k.weight", {H, H, 1}),
-                     *wv = get(a + ".conv_v.weight", {H, H, 1}), *bq = get(a + ".conv_q.bias", {H}),
-                     *bk = get(a + ".conv_k.bias", {H}), *bv = get(a + ".conv_v.bias", {H});
-    if (!wq || !wk || !wv || !bq || !bk || !bv) break;
-    const HostTensor* ws3[3] = {wq, wk, wv};
-    const HostTensor* bs3[3] = {bq, bk, bv};
-    // q | k | v stacked into one 1x1 conv H -> 3H (attentions.py:263-265)
-    L.qkv.push_back(pack_tc(c, 3 * H, H, 1, 1, [&](int n, int ci, int) { return ws3[n / H]->data[(size_t)(n % H) * H + ci]; },
-                            [&](int n) { return bs3[n / H]->data[n % H]; }));
-    L.o.push_back(dense(a + ".conv_o", H, H, 1));
-    L.relk.push_back(put(get(a + ".emb_rel_k", {1, 2 * L.window + 1, dk})));
-    L.relv.push_back(put(get(a + ".emb_rel_v", {1, 2 * L.window + 1, dk})));
-    const std::string e = "enc_p.encoder.";
-    L.ln1g.push_back(put(get(e + "norm_layers_1." + std::to_string(i) + ".gamma", {H})));
-    L.ln1b.push_back(put(get(e + "norm_layers_1." + std::to_string(i) + ".beta", {H})));
-    L.ln2g.push_back(put(get(e + "norm_layers_2." + std::to_string(i) + ".gamma", {H})));
-    L.ln2b.push_back(put(get(e + "norm_layers_2." + std::to_string(i) + ".beta", {H})));
-    L.ffn1.push_back(dense32(e + "ffn_layers." + std::to_string(i) + ".conv_1", L.Fc, H, fk));
-    L.ffn2.push_back(dense32(e + "ffn_layers." + std::to_string(i) + ".conv_2", H, L.Fc, fk));
-  }
-  L.proj = dense("enc_p.proj", 2 * L.C, H, 1);
-  // DurationPredictor
-  L.dp_c1 = dense32("dp.conv_1", L.D, H, 3);
-  L.dp_c2 = dense32("dp.conv_2", L.D, L.D, 3);
-  L.dp_n1g = put(get("dp.norm_1.gamma", {L.D})); L.dp_n1b = put(get("dp.norm_1.beta", {L.D}));
-  L.dp_n2g = put(get("dp.norm_2.gamma", {L.D})); L.dp_n2b = put(get("dp.norm_2.beta", {L.D}));
-  L.dp_pw = put(get("dp.proj.weight", {1, L.D, 1})); L.dp_pb = put(get("dp.proj.bias", {1}));
-  L.dp_cw = put(get("dp.cond.weight", {H, G, 1})); L.dp_cb = put(get("dp.cond.bias", {H}));
-  // StochasticDurationPredictor, reverse path
-  L.sdp_pre = dense("sdp.pre", H, H, 1);
-  L.sdp_proj = dense("sdp.proj", H, H, 1);
-  L.sdp_cw = put(get("sdp.cond.weight", {H, G, 1})); L.sdp_cb = put(get("sdp.cond.bias", {H}));
-  {
-    const HostTensor* m = get("sdp.flows.0.m", {2, 1});
-    const HostTensor* lg = get("sdp.flows.0.logs", {2, 1});
-    if (m && lg) {
-      HostTensor t; t.shape = {2}; t.data = {m->data[0], lg->data[0]};   // logw is channel 0 (models.py:178-179)
-      L.ea = put(&t);
-    }
-  }
-  for (int j = 0; j < 4; ++j) {
-    const std::string p = j == 0 ? std::string("sdp.convs") : "sdp.flows." + std::to_string(2 * j + 1) + ".convs";
-    DdsLayers& d = L.dds[j];
-    for (int i = 0; i < 3; ++i) {
-      const std::string n = std::to_string(i);
-      d.sep_w[i] = put(get(p + ".convs_sep." + n + ".weight", {H, 1, 3}));
-      d.sep_b[i] = put(get(p + ".convs_sep." + n + ".bias", {H}));
-      d.n1g[i] = put(get(p + ".norms_1." + n + ".gamma", {H})); d.n1b[i] = put(get(p + ".norms_1." + n + ".beta", {H}));
-      d.n2g[i] = put(get(p + ".norms_2." + n + ".gamma", {H})); d.n2b[i] = put(get(p + ".norms_2." + n + ".beta", {H}));
-      d.c1x1[i] = dense(p + ".convs_1x1." + n, H, H, 1);
-    }
-    if (j > 0) {
-      const std::string f = "sdp.flows." + std::to_string(2 * j + 1);
-      L.cf_pre_w[j] = put(get(f + ".pre.weight", {H, 1, 1})); L.cf_pre_b[j] = put(get(f + ".pre.bias", {H}));
-      L.cf_pw[j] = put(get(f + ".proj.weight", {ovc_tts::NP, H, 1})); L.cf_pb[j] = put(get(f + ".proj.bias", {ovc_tts::NP}));
-    }
-  }
-  if (!err.empty()) return fail(OVC_ERR_MISSING, "%s", err.c_str());
-  L.ready = true;
-  return OVC_OK;
-}
+#include "ovc_tts_pack.inc"   // pack_tts(): V1 TTS front-half weights (text encoder, duration predictors, emb_g)
 
 static int finalize(ovc_ctx* c) {
   const ovc_hparams& hp = c->hp;
@@ -1343,259 +1198,7 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
   return run_dec(r, W, ws, cond, lens, o_hat);
 }
 
-// ---------------------------------------------------------------------------------------------
-// V1 TTS front half (SynthesizerTrn.infer, models.py:467-490)
-// ---------------------------------------------------------------------------------------------
-struct TtsWs {   // float offsets into c->d_tts; rows R = B * T, channels-last
-  size_t g, cv, X, QKV, S, A, Y, F, STATS, DX, D1, D2, SX, XC, HH, Y1, Y2, z0, z1, lws, lwd, logw, wceil, cum, ylen, CT0, CT1, CT2,
-      total;
-  int P;   // time pitch of the [C][P] copies (multiple of 4)
-};
-static TtsWs tts_ws_layout(const ovc_ctx* c, int B, int T) {
-  const TtsLayers& L = c->tts;
-  const size_t R = (size_t)B * T;
-  TtsWs W;
-  size_t o = 0;
-  auto take = [&](size_t n) { size_t r = o; o = round_up(o + n, 64); return r; };
-  W.g = take((size_t)B * c->hp.gin_channels);
-  W.cv = take((size_t)B * L.H);
-  W.X = take(R * L.H); W.QKV = take(R * 3 * L.H); W.S = take((size_t)B * L.heads * T * T);
-  W.A = take(R * L.H); W.Y = take(R * L.H); W.F = take(R * L.Fc); W.STATS = take(R * 2 * L.C);
-  W.DX = take(R * L.H); W.D1 = take(R * L.D); W.D2 = take(R * L.D);
-  W.SX = take(R * L.H); W.XC = take(R * L.H); W.HH = take(R * L.H); W.Y1 = take(R * L.H); W.Y2 = take(R * L.H);
-  W.z0 = take(R); W.z1 = take(R); W.lws = take(R); W.lwd = take(R); W.logw = take(R); W.wceil = take(R);
-  W.cum = take(R);                 // int32
-  W.ylen = take((size_t)2 * B + 4);   // int64
-  W.P = (int)round_up((size_t)T, 4);
-  const size_t widest = (size_t)std::max(std::max(L.Fc, L.D), L.H);
-  W.CT0 = take((size_t)B * widest * W.P); W.CT1 = take((size_t)B * widest * W.P); W.CT2 = take((size_t)B * widest * W.P);
-  W.total = o;
-  return W;
-}
-
-static int tts_tap(Run& r, const char* name, const float* src, int C) {   // channels-last [B][T][C] -> shape (B, T, C, C)
-  return tap(r, name, src, r.Tmax, C, C);
-}
-
-// text -> durations.  Leaves m_p / logs_p (STATS), cumulative durations, y_lengths and g in c->d_tts.
-static int run_tts_encode(ovc_ctx* c, const long long* tokens, const long long* lens, const long long* sid,
-                          const float* noise_w, uint64_t seed, float noise_scale_w, float length_scale, float sdp_ratio, int B,
-                          int T, long long* y_lengths, float* w_ceil_out, float* logw_out, cudaStream_t st) {
-  const TtsLayers& L = c->tts;
-  const TtsWs W = tts_ws_layout(c, B, T);
-  if (W.total > c->tts_floats) {
-    CK(cudaStreamSynchronize(st));
-    if (c->d_tts) CK(cudaFree(c->d_tts));
-    c->d_tts = nullptr; c->tts_floats = 0;
-    if (cudaMalloc(&c->d_tts, W.total * sizeof(float)) != cudaSuccess) {
-      cudaGetLastError();
-      return fail(OVC_ERR_NOMEM, "TTS workspace of %.2f GB for B=%d T=%d does not fit", W.total * 4e-9, B, T);
-    }
-    c->tts_floats = W.total;
-  }
-  c->tts_B = 0;
-  float* ws = c->d_tts;
-  const float* P = c->d_w;          // fp32 parameter arena
-  Run r{c, st, B, T, T, lens, lens, (double)B * T};
-  c->launches = 0;
-  const int H = L.H, G = c->hp.gin_channels;
-  const dim3 gE((T * H + 255) / 256, B), gRow((T + 63) / 64, B);
-  // OVC_TTS_SIMPLE=1: the one-thread-per-element reference kernels (CPU-checked element functions) instead of the
-  // warp-cooperative LayerNorm / fused attention; also the fallback when the logits of 8 queries exceed 48 KB of smem
-  static const bool simple = getenv("OVC_TTS_SIMPLE") && atoi(getenv("OVC_TTS_SIMPLE")) != 0;
-  const size_t att_smem = sizeof(float) * ((size_t)TTS_ATT_Q * T + (size_t)TTS_ATT_Q * (H / L.heads));
-  TcExtra tx; tx.use_lens_frames = true;
-  auto dense = [&](const TcLayer& lay, const float* x, float* y, float slope) -> int {
-    return launch_tc(r, lay, x, y, nullptr, T, 1, slope, 1.f, 0, 0, tx);
-  };
-  // ---- the k = 3 convs in fp32.  Fast path: rows -> [C][P], FFMA2 conv kernel(s), -> rows; a chain of convs (the FFN)
-  // stays in [C][P] between its members.  relu before a conv = its input leaky-relu with slope 0.
-  Run rc{c, st, B, T, W.P, lens, lens, (double)B * T};
-  float* CT[3] = {ws + W.CT0, ws + W.CT1, ws + W.CT2};
-  auto to_ct = [&](const float* x, int C, float* out) -> int {
-    TRY(prof_begin(r));
-    tts_to_ct_kernel<<<dim3((W.P + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st>>>(x, lens, T, C, W.P, out);
-    CK(cudaGetLastError());
-    c->launches++;
-    return prof_end(r, V_TRANSPOSE, 0, 0.0, 8.0 * C * (double)B * T);
-  };
-  auto from_ct = [&](const float* in, int C, float* out) -> int {
-    TRY(prof_begin(r));
-    tts_from_ct_kernel<<<dim3((W.P + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st>>>(in, lens, T, C, W.P, out);
-    CK(cudaGetLastError());
-    c->launches++;
-    return prof_end(r, V_TRANSPOSE, 0, 0.0, 8.0 * C * (double)B * T);
-  };
-  auto conv_ct = [&](const TtsLayers::Fp32Dense& d, const float* x, float* y, int relu_in) -> int {
-    ConvArgs a{};
-    a.x = x; a.x_bs = (long long)d.Cin * W.P; a.x_pitch = W.P;
-    a.bias = P + d.cl.b_off; a.bias_bs = 0;
-    a.y = y; a.y_bs = (long long)d.N * W.P; a.y_pitch = W.P;
-    a.lens_in = lens; a.lens_out = lens; a.mul_in = 1; a.mul_out = 1;
-    a.slope = relu_in ? 0.f : 1.f; a.scale = 1.f;
-    return launch(rc, d.cl, a, T);
-  };
-  auto dense32 = [&](const TtsLayers::Fp32Dense& d, const float* x, float* y, int relu_in) -> int {
-    if (d.fast) {
-      TRY(to_ct(x, d.Cin, CT[0]));
-      TRY(conv_ct(d, CT[0], CT[1], relu_in));
-      return from_ct(CT[1], d.N, y);
-    }
-    TRY(prof_begin(r));
-    tts_dense_kernel<<<dim3((T * d.N + 255) / 256, B), 256, 0, st>>>(x, lens, P + d.w, P + d.b, T, d.Cin, d.K, d.N, relu_in, y);
-    CK(cudaGetLastError());
-    c->launches++;
-    return prof_end(r, V_TTS_DENSE, 0, 2.0 * d.Cin * d.K * d.N * (double)B * T, 4.0 * (d.Cin + d.N) * (double)B * T);
-  };
-  auto ln = [&](const float* a, const float* rr, const float* res, size_t g_off, size_t b_off, int C, int pre, int post,
-                float* out) -> int {
-    TRY(prof_begin(r));
-    if (simple) tts_ln_kernel<<<gRow, 64, 0, st>>>(a, rr, res, P + g_off, P + b_off, lens, T, C, pre, post, out);
-    else tts_ln_warp_kernel<<<dim3((T + 3) / 4, B), 128, 0, st>>>(a, rr, res, P + g_off, P + b_off, lens, T, C, pre, post, out);
-    CK(cudaGetLastError());
-    c->launches++;
-    return prof_end(r, V_TTS_LN, 0, 0.0, 0.0);
-  };
-#define TTS_RUN(V, ...)                       \
-  do {                                        \
-    TRY(prof_begin(r));                       \
-    __VA_ARGS__;                              \
-    CK(cudaGetLastError());                   \
-    c->launches++;                            \
-    TRY(prof_end(r, V, 0, 0.0, 0.0));         \
-  } while (0)
-
-  float *X = ws + W.X, *QKV = ws + W.QKV, *S = ws + W.S, *A = ws + W.A, *Y = ws + W.Y, *F = ws + W.F, *g = ws + W.g;
-  TTS_RUN(V_TTS_MISC, tts_speaker_kernel<<<dim3((G + 127) / 128, B), 128, 0, st>>>(P + L.emb_g, sid, L.n_speakers, G, g));
-  // ---- TextEncoder (models.py:47-57)
-  TTS_RUN(V_TTS_MISC, tts_embed_kernel<<<gE, 256, 0, st>>>(tokens, lens, P + L.emb, L.n_vocab, T, H, sqrtf((float)H), X));
-  for (int i = 0; i < L.n_layers; ++i) {
-    // MultiHeadAttention (attentions.py:262-324): QKV projection and output projection on the tensor cores
-    TRY(dense(L.qkv[i], X, QKV, 1.f));
-    if (simple || att_smem > 48 * 1024 || (H / L.heads) % 4 != 0) {
-      TTS_RUN(V_TTS_SCORES, tts_scores_kernel<<<dim3((T * T + 255) / 256, L.heads, B), 256, 0, st>>>(QKV, lens, P + L.relk[i], T, H, L.heads, L.window, S));
-      TTS_RUN(V_TTS_ATTN, tts_attn_out_kernel<<<gE, 256, 0, st>>>(S, QKV, lens, P + L.relv[i], T, H, L.heads, L.window, A));
-    } else {
-      TTS_RUN(V_TTS_ATTN, tts_attention_kernel<<<dim3((T + TTS_ATT_Q - 1) / TTS_ATT_Q, L.heads, B), 128, att_smem, st>>>(
-                              QKV, lens, P + L.relk[i], P + L.relv[i], T, H, L.heads, L.window, A));
-    }
-    TRY(dense(L.o[i], A, Y, 1.f));
-    TRY(ln(X, Y, nullptr, L.ln1g[i], L.ln1b[i], H, 0, 0, X));                  // attentions.py:115
-    // FFN (attentions.py:439-448): conv k, relu (as the next conv's input activation), conv k -- fp32 CUDA cores
-    if (L.ffn1[i].fast && L.ffn2[i].fast) {
-      TRY(to_ct(X, H, CT[0]));
-      TRY(conv_ct(L.ffn1[i], CT[0], CT[1], 0));
-      TRY(conv_ct(L.ffn2[i], CT[1], CT[2], 1));
-      TRY(from_ct(CT[2], H, Y));
-    } else {
-      TRY(dense32(L.ffn1[i], X, F, 0));
-      TRY(dense32(L.ffn2[i], F, Y, 1));
-    }
-    TRY(ln(X, Y, nullptr, L.ln2g[i], L.ln2b[i], H, 0, 0, X));                  // attentions.py:119
-    if (i == 0) TRY(tts_tap(r, "tts.layer0", X, H));
-  }
-  TRY(tts_tap(r, "tts.x", X, H));
-  TRY(dense(L.proj, X, ws + W.STATS, 1.f));                                     // models.py:54
-  TRY(tts_tap(r, "tts.stats", ws + W.STATS, 2 * L.C));
-
-  // ---- DurationPredictor (models.py:86-100)
-  float *DX = ws + W.DX, *D1 = ws + W.D1, *D2 = ws + W.D2, *cv = ws + W.cv;
-  TTS_RUN(V_TTS_MISC, tts_lin_kernel<<<dim3((H + 127) / 128, B), 128, 0, st>>>(g, P + L.dp_cw, P + L.dp_cb, G, H, cv));
-  TTS_RUN(V_TTS_MISC, tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(X, cv, lens, T, H, DX));
-  TRY(dense32(L.dp_c1, DX, D1, 0));
-  TRY(ln(D1, nullptr, nullptr, L.dp_n1g, L.dp_n1b, L.D, 1, 0, D1));
-  TRY(dense32(L.dp_c2, D1, D2, 0));
-  TRY(ln(D2, nullptr, nullptr, L.dp_n2g, L.dp_n2b, L.D, 1, 0, D2));
-  const dim3 gT((T + 127) / 128, B);
-  TTS_RUN(V_TTS_MISC, tts_logw_kernel<<<gT, 128, 0, st>>>(D2, lens, P + L.dp_pw, P + L.dp_pb, T, L.D, 0, ws + W.lwd));
-
-  // ---- StochasticDurationPredictor, reverse (models.py:135-143, 170-180)
-  float *SX = ws + W.SX, *XC = ws + W.XC, *HH = ws + W.HH, *Y1 = ws + W.Y1, *Y2 = ws + W.Y2;
-  auto dds = [&](int j, float* h) -> int {                                      // DDSConv.forward, modules.py:115-130
-    const DdsLayers& d = L.dds[j];
-    int dil = 1;
-    for (int i = 0; i < 3; ++i, dil *= 3) {
-      TTS_RUN(V_TTS_DW, tts_dwconv_kernel<<<gE, 256, 0, st>>>(h, lens, P + d.sep_w[i], P + d.sep_b[i], T, H, dil, Y1));
-      TRY(ln(Y1, nullptr, nullptr, d.n1g[i], d.n1b[i], H, 0, 1, Y1));
-      TRY(dense(d.c1x1[i], Y1, Y2, 1.f));
-      TRY(ln(Y2, nullptr, h, d.n2g[i], d.n2b[i], H, 0, 1, h));
-    }
-    return OVC_OK;
-  };
-  TRY(dense(L.sdp_pre, X, SX, 1.f));
-  TTS_RUN(V_TTS_MISC, tts_lin_kernel<<<dim3((H + 127) / 128, B), 128, 0, st>>>(g, P + L.sdp_cw, P + L.sdp_cb, G, H, cv));
-  TTS_RUN(V_TTS_MISC, tts_add_rowvec_kernel<<<gE, 256, 0, st>>>(SX, cv, lens, T, H, SX));
-  TRY(dds(0, SX));
-  TRY(dense(L.sdp_proj, SX, XC, 1.f));
-  TRY(tts_tap(r, "tts.sdp_cond", XC, H));
-  float *za = ws + W.z0, *zb = ws + W.z1;
-  TTS_RUN(V_TTS_MISC, tts_noise_w_kernel<<<gT, 128, 0, st>>>(noise_w, seed, noise_scale_w, T, za, zb));
-  for (int j = 3; j >= 1; --j) {
-    std::swap(za, zb);                                                          // Flip (modules.py:375-376)
-    TTS_RUN(V_TTS_MISC, tts_cf_pre_kernel<<<gE, 256, 0, st>>>(za, P + L.cf_pre_w[j], P + L.cf_pre_b[j], XC, lens, T, H, HH));
-    TRY(dds(j, HH));
-    TTS_RUN(V_TTS_SPLINE, tts_cf_tail_kernel<<<gRow, 64, 0, st>>>(HH, lens, P + L.cf_pw[j], P + L.cf_pb[j], zb, T, H, 5.0f));   // tail_bound, modules.py:467
-  }
-  std::swap(za, zb);
-  TTS_RUN(V_TTS_MISC, tts_logw_kernel<<<gT, 128, 0, st>>>(za, lens, P + L.ea, nullptr, T, 1, 1, ws + W.lws));
-  // ---- durations (models.py:474-481)
-  long long* ylen = reinterpret_cast<long long*>(ws + W.ylen);
-  int* cum = reinterpret_cast<int*>(ws + W.cum);
-  TTS_RUN(V_TTS_MISC, tts_durations_kernel<<<(B + 63) / 64, 64, 0, st>>>(ws + W.lws, ws + W.lwd, lens, sdp_ratio, length_scale, B, T, ws + W.logw,
-                                                     ws + W.wceil, cum, ylen));
-#undef TTS_RUN
-  if (c->debug) {
-    Run r1{c, st, B, T, T, lens, lens, 0.0};
-    TRY(tap(r1, "tts.logw_sdp", ws + W.lws, 1, T, T));
-    TRY(tap(r1, "tts.logw_dp", ws + W.lwd, 1, T, T));
-  }
-  CK(cudaMemcpyAsync(y_lengths, ylen, (size_t)B * sizeof(long long), cudaMemcpyDeviceToDevice, st));
-  if (w_ceil_out) CK(cudaMemcpyAsync(w_ceil_out, ws + W.wceil, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (logw_out) CK(cudaMemcpyAsync(logw_out, ws + W.logw, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  c->tts_B = B;
-  c->tts_T = T;
-  return OVC_OK;
-}
-
-// durations -> waveform: expand m_p / logs_p along the path, sample z_p, flow reverse, generator (models.py:482-490)
-static int run_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int max_len,
-                          int ragged, float* o, float* z_out, float* zp_out, cudaStream_t st) {
-  const TtsLayers& L = c->tts;
-  const int T = c->tts_T;
-  const TtsWs TW = tts_ws_layout(c, B, T);
-  const WsLayout W = ws_layout(c, B, Ymax);
-  TRY(ensure_ws(c, W, B, Ymax, st));
-  float* ws = c->d_ws;
-  const long long* ylen = reinterpret_cast<const long long*>(c->d_tts + TW.ylen);
-  Run r{c, st, B, Ymax, W.P, ylen, ragged ? ylen : nullptr, (double)B * Ymax};
-  c->launches = 0;
-  {
-    dim3 grid((W.P + 127) / 128, L.C, B);
-    tts_expand_kernel<<<grid, 128, 0, st>>>(c->d_tts + TW.STATS, reinterpret_cast<const int*>(c->d_tts + TW.cum), ylen, noise,
-                                            (long long)L.C * Ymax, Ymax, seed, noise_scale, T, L.C, Ymax, W.P, ws + W.z);
-    CK(cudaGetLastError());
-    c->launches++;
-  }
-  TRY(copy_latent_out(r, W, ws, zp_out));
-  {
-    CondArgs a;   // g conditions the flow (as g_tgt) and the generator (models.py:488-489)
-    a.w = c->d_w + c->cond_w_off; a.bias = c->d_w + c->cond_b_off;
-    a.w_row = c->d_cond_wrow; a.sel = c->d_cond_sel;
-    a.g_src = c->d_tts + TW.g; a.g_tgt = c->d_tts + TW.g; a.out = ws + W.cond;
-    a.rows_out = c->cond_rows_out; a.gin = c->hp.gin_channels;
-    dim3 grid((c->cond_rows_out + 7) / 8, B);
-    cond_kernel<<<grid, 256, 0, st>>>(a);
-    CK(cudaGetLastError());
-    c->launches++;
-  }
-  const float* cond = ws + W.cond;
-  TRY(run_flow(r, W, ws, true, cond));
-  TRY(copy_latent_out(r, W, ws, z_out));
-  // o = dec((z * y_mask)[:, :, :max_len]) (models.py:489): the flow above saw every frame, only the generator is cut
-  Run rd = r;
-  if (max_len > 0 && max_len < Ymax) rd.Tmax = max_len;
-  return run_dec(rd, W, ws, cond, ylen, o);
-}
+#include "ovc_tts_run.inc"    // run_tts_encode() / run_tts_decode(): SynthesizerTrn.infer on the device
 
 }  // namespace ovc
 
