@@ -5,8 +5,8 @@
 
 A "step" is one pass of the hot path over one batch of synthetic utterances.  The default
 workload is BASELINE.json configs[1]: batch 32 x 10 s clips at 22.05 kHz on one B200, in the
-default arithmetic mode (--precision tf32x3: split-precision tensor-core convolutions, fp32-grade
-results -- stricter than the config's "fp16"; fp32 = CUDA cores only, tf32 = single pass).  The
+default arithmetic mode (--precision f16x3: split-precision fp16 tensor-core convolutions, fp32-grade
+results -- stricter than the config's "fp16"; fp32 = CUDA cores only, f16 = single pass).  The
 other modes are timed briefly in the same run and reported under "modes_audio_s_per_s".  For N > 1 launch under torchrun: one rank per
 GPU, every rank converts its own `batch` clips (weak scaling, no data-path collective; NCCL only
 broadcasts the checkpoint and, in the end-to-end leg, gathers the output waveforms on rank 0).
@@ -201,9 +201,10 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU reference arm")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips in the cpu_baseline sample of the native arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("OVC_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "tf32"],
-                    help="generator conv arithmetic: tf32x3 = split-precision tensor cores (default, fp32-grade), "
-                         "fp32 = CUDA-core FFMA2, tf32 = single-pass TF32 (the reference's own GPU default)")
+    ap.add_argument("--precision", default=os.environ.get("OVC_PRECISION", "f16x3"), choices=["fp32", "f16x3", "f16"],
+                    help="conv arithmetic: f16x3 = split-precision fp16 tensor cores (default, fp32-grade), "
+                         "fp32 = CUDA-core FFMA2, f16 = single-pass fp16 (11-bit operands, the reference's own GPU default class)")
+    ap.add_argument("--wide-variant", type=int, default=None, help="tiling of the 128-column tensor-core kernel (ovc_set_option)")
     ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE config-3 side measurement (V1 TTS + convert, batch 16)")
     ap.add_argument("--no-modes", action="store_true", help="skip the short side measurements of the other precisions")
     args = ap.parse_args()
@@ -245,6 +246,8 @@ def main():
         conv = ToneColorConverter(cfg, device=dev, enable_watermark=False, precision=args.precision)
     conv.model.load_state_dict(sd)
     del sd
+    if args.wide_variant is not None:
+        conv.model.native.set_option("wide_variant", args.wide_variant)
 
     B, secs = args.batch, args.secs
     waves = [synth_wave(rank * B + i, secs) for i in range(B)]
@@ -295,7 +298,7 @@ def main():
     # ---- the other arithmetic modes, short (2 timed steps), device-resident only
     modes = {}
     if not args.no_modes:
-        for mode in ("fp32", "tf32x3", "tf32"):
+        for mode in ("fp32", "f16x3", "f16"):
             if mode == args.precision:
                 continue
             native.set_precision(mode)
@@ -369,7 +372,7 @@ def main():
     else:
         # tensor-core modes: the MMA rate is what binds.  TF32 runs at half the bf16 rate; every algorithmic FLOP
         # costs 3 tensor FLOPs in the split-precision mode.
-        passes = 3 if args.precision == "tf32x3" else 1
+        passes = 3 if args.precision == "f16x3" else 1
         tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
         tc_traffic, tc_note = None, None
         try:   # dram bytes of a representative launch of this kernel from the committed ncu --set full capture
@@ -394,8 +397,8 @@ def main():
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split-precision tensor-core generator convs, fp32 FFMA2 elsewhere)",
-                  "tf32": "tf32 (single-pass tensor-core generator convs, fp32 elsewhere)"}[args.precision],
+        "dtype": {"fp32": "f32", "f16x3": "f32 (3xFP16 split-precision tensor-core convs with fp32 accumulation, fp32 FFMA2 elsewhere)",
+                  "f16": "f16 operands, f32 accumulation (single-pass tensor-core convs, fp32 elsewhere)"}[args.precision],
         "data": "synthetic", "precision": args.precision, "modes_audio_s_per_s": modes,
         "config": {"workload": f"ToneColorConverter.convert_batch, batch {B} x {secs:g} s clips @ {SR} Hz per GPU "
                                "(BASELINE configs[1]), seeded synthetic checkpoint, tau 0.3, in-kernel Philox noise",

@@ -166,14 +166,27 @@ OVC_API int ovc_tts_encode(ovc_ctx* ctx, const int64_t* tokens, const int64_t* x
 OVC_API int ovc_tts_decode(ovc_ctx* ctx, const float* noise, uint64_t seed, float noise_scale, int B, int Ymax, int max_len,
                            int ragged, float* o, float* z, float* z_p, void* stream);
 
-/* Arithmetic of the generator's ResBlock convolutions (90 % of the FLOPs):
- *   0 (default)  fp32 FFMA2 on the CUDA cores
- *   1            split-precision 3xTF32 on the 5th-gen tensor cores (tcgen05 + TMEM): every product is
- *                a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with tf32-exact high parts, fp32 accumulation --
- *                fp32-grade error (3e-5 of the output rms measured), same parity gate as mode 0
- *   2            single-pass TF32 on the tensor cores: the precision the REFERENCE itself gets on a GPU by
- *                default (torch.backends.cudnn.allow_tf32 = True); ~4e-3 of the output rms, own looser gate */
+/* Arithmetic of the convolutions (generator ResBlocks = 90 % of the FLOPs, WaveNet stacks, upsamplers):
+ *   0            fp32 FFMA2 on the CUDA cores
+ *   1 (default of the Python surface)  split-precision "3xFP16" on the 5th-gen tensor cores (tcgen05 + TMEM):
+ *                x = hi + lo / 2^11 with hi = fp16(x), lo = fp16((x - hi) * 2^11); every product is
+ *                a_hi*b_hi + (a_lo*b_hi + a_hi*b_lo) / 2^11, fp32 accumulation, cross terms in their own
+ *                accumulator -- fp32-grade error, same parity gate as mode 0.  Operands must be < 65504 in magnitude.
+ *   2            single-pass fp16 on the tensor cores (11-bit operands): the precision class the REFERENCE itself
+ *                gets on a GPU by default (cuDNN TF32, torch.backends.cudnn.allow_tf32 = True); own looser gate */
 OVC_API int ovc_set_precision(ovc_ctx* ctx, int mode);
+
+/* Tuning / diagnostics switches (never change results beyond fp32 reordering):
+ *   OVC_OPT_WIDE_VARIANT  tiling of the 128-column tensor-core kernel: 0 (default) 128-step tiles, two CTAs per SM,
+ *                         2-CTA clusters multicasting the weight stream; 1: 256-step tiles, one CTA per SM; 2: as 0
+ *                         without clusters
+ *   OVC_OPT_TTS_SIMPLE    1: one-thread-per-element text-side kernels (the CPU-checked element functions) instead of
+ *                         the warp-cooperative LayerNorm / fused attention
+ *   OVC_OPT_GRAPH         1 (default): replay the launch sequence of a repeated (shape, buffers) call from a CUDA graph */
+#define OVC_OPT_WIDE_VARIANT 1
+#define OVC_OPT_TTS_SIMPLE 2
+#define OVC_OPT_GRAPH 3
+OVC_API int ovc_set_option(ovc_ctx* ctx, int key, int value);
 
 /* Number of kernels the last ovc_voice_conversion / ovc_convert_waveform call launched. */
 OVC_API int ovc_last_launch_count(const ovc_ctx* ctx);

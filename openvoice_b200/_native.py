@@ -19,7 +19,7 @@ EXPORTS = (
     "ovc_finalize_weights", "ovc_workspace_floats", "ovc_voice_conversion", "ovc_last_launch_count",
     "ovc_profile_enable", "ovc_profile_read", "ovc_profile_detail", "ovc_debug_enable", "ovc_debug_fetch",
     "ovc_spectrogram", "ovc_convert_waveform", "ovc_set_precision", "ovc_reference_encoder",
-    "ovc_tts_info", "ovc_tts_encode", "ovc_tts_decode",
+    "ovc_tts_info", "ovc_tts_encode", "ovc_tts_decode", "ovc_set_option",
 )
 
 
@@ -33,6 +33,9 @@ class OvcHParams(C.Structure):
         ("upsample_kernel_sizes", C.c_int32 * 4), ("upsample_initial_channel", C.c_int32),
         ("zero_g", C.c_int32), ("hop_length", C.c_int32),
     ]
+
+
+PRECISIONS = {"fp32": 0, "f16x3": 1, "f16": 2}
 
 
 class OvcError(RuntimeError):
@@ -68,6 +71,7 @@ def load_library(path: Optional[str] = None):
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ovc_last_launch_count.argtypes = [C.c_void_p]
     lib.ovc_set_precision.argtypes = [C.c_void_p, C.c_int]
+    lib.ovc_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.ovc_reference_encoder.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ovc_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.ovc_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
@@ -181,10 +185,15 @@ class NativeConverter:
         self.finalized = True
 
     def set_precision(self, mode: str):
-        """'fp32' (CUDA-core FFMA2, default) or 'tf32x3' (split-precision tensor-core ResBlock convs)."""
-        m = {"fp32": 0, "tf32x3": 1, "tf32": 2}[mode]
+        """'fp32' (CUDA-core FFMA2), 'f16x3' (split-precision fp16 tensor-core convs, fp32-grade) or 'f16' (single pass)."""
+        m = PRECISIONS[mode]
         _check(self.lib, self.lib.ovc_set_precision(self.handle, m), "ovc_set_precision")
         self.precision = mode
+
+    def set_option(self, key: str, value: int):
+        """Tuning switches of include/ovc.h: 'wide_variant' (0/1/2), 'tts_simple' (0/1), 'graph' (0/1)."""
+        k = {"wide_variant": 1, "tts_simple": 2, "graph": 3}[key]
+        _check(self.lib, self.lib.ovc_set_option(self.handle, k, int(value)), "ovc_set_option")
 
     # ---- hot path --------------------------------------------------------------------------
     def voice_conversion(self, spec, lengths, g_src, g_tgt, noise=None, tau: float = 0.3, seed: int = 0,

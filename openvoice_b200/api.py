@@ -76,9 +76,9 @@ class NativeSynthesizer:
 
     def __init__(self, hps, device: str, precision: Optional[str] = None):
         """``precision``: arithmetic of the generator's ResBlock / upsampling convolutions --
-        ``"tf32x3"`` (default; split-precision tcgen05 tensor cores, fp32-grade: 3e-5 of the output rms),
-        ``"fp32"`` (CUDA-core FFMA2 everywhere, 8e-6) or ``"tf32"`` (single-pass TF32, what the reference
-        itself gets on a GPU through cuDNN's allow_tf32 default; ~1e-2).  Env override: OVC_PRECISION."""
+        ``"f16x3"`` (default; split-precision fp16 on the tcgen05 tensor cores, fp32-grade),
+        ``"fp32"`` (CUDA-core FFMA2 everywhere) or ``"f16"`` (single-pass fp16: the 11-bit operand precision the
+        reference itself gets on a GPU through cuDNN's allow_tf32 default; ~1e-2).  Env override: OVC_PRECISION."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("openvoice_b200 runs on CUDA (sm_100a) only; there is no CPU path")
@@ -88,7 +88,7 @@ class NativeSynthesizer:
         self.n_speakers = int(getattr(hps.data, "n_speakers", 0))
         index = dev.index if dev.index is not None else torch.cuda.current_device()
         self.native = NativeConverter(hps, index)
-        self.precision = precision or os.environ.get("OVC_PRECISION", "tf32x3")
+        self.precision = precision or os.environ.get("OVC_PRECISION", "f16x3")
         self.native.set_precision(self.precision)
         self.spec_channels = hps.data.filter_length // 2 + 1
         self.ref_enc = ReferenceEncoder(self.native, self.spec_channels, int(getattr(hps.model, "gin_channels", 256)))

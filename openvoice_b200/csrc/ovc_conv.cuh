@@ -93,8 +93,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// A wait that cannot complete is a protocol bug: trap after ~2 s instead of hanging the device (the launch then fails
+// with an error the host reports), cost: one clock read per FAILED poll.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier.

@@ -16,12 +16,6 @@
 #include "../../include/ovc.h"
 #include "ovc_small.cuh"
 #include "ovc_tcconv.cuh"
-#ifndef OVC_TC_PAIR
-#define OVC_TC_PAIR 0   // 1: wide layers on CTA pairs (ovc_tcconv_pair.cuh) -- experimental, not in the default build
-#endif
-#if OVC_TC_PAIR
-#include "ovc_tcconv_pair.cuh"
-#endif
 #include "ovc_tts.cuh"
 #include "ovc_refenc.cuh"
 #include "ovc_variants.h"
@@ -104,22 +98,23 @@ struct WNLayers {
 // V1 TTS front half (TextEncoder / DurationPredictor / StochasticDurationPredictor, models.py:16-180): dense convs
 // as tensor-core layers, small fp32 parameters as offsets into the fp32 arena.  Hyper-parameters are read off the
 // checkpoint shapes (the reference takes them from config.json: api.py:26-31, models.py:451-465).
+// k = 3 convs and the whole duration chain stay on the CUDA cores in plain fp32: the FFMA2 conv kernel on a [C][T]
+// copy when the shape fits a variant (k 3, N % 64 == 0: every released checkpoint), else the one-thread-per-output
+// kernel (sequential fmaf chain over w [K][Cin][N])
+struct Fp32Dense { size_t w = 0, b = 0; int Cin = 0, K = 0, N = 0; bool fast = false; ConvLayer cl; };
 struct DdsLayers {            // DDSConv, modules.py:84-113
   size_t sep_w[3] = {0}, sep_b[3] = {0}, n1g[3] = {0}, n1b[3] = {0}, n2g[3] = {0}, n2b[3] = {0};
-  TcLayer c1x1[3];
+  Fp32Dense c1x1[3];          // fp32: the spline inverses downstream amplify conditioning errors up to 1e3 x
 };
 struct TtsLayers {
   bool ready = false;
   int n_vocab = 0, n_speakers = 0, H = 0, C = 0, Fc = 0, heads = 0, n_layers = 0, window = 0, D = 0;
   size_t emb = 0, emb_g = 0;
-  // k = 3 convs kept on the CUDA cores: the FFMA2 conv kernel on a [C][T] copy when the shape fits a variant
-  // (k 3, N % 64 == 0: every released checkpoint), else the one-thread-per-output kernel on w [K][Cin][N]
-  struct Fp32Dense { size_t w = 0, b = 0; int Cin = 0, K = 0, N = 0; bool fast = false; ConvLayer cl; };
   std::vector<TcLayer> qkv, o;
   std::vector<Fp32Dense> ffn1, ffn2;
   std::vector<size_t> relk, relv, ln1g, ln1b, ln2g, ln2b;
-  TcLayer proj, sdp_pre, sdp_proj;
-  Fp32Dense dp_c1, dp_c2;
+  TcLayer proj;
+  Fp32Dense dp_c1, dp_c2, sdp_pre, sdp_proj;
   size_t dp_n1g = 0, dp_n1b = 0, dp_n2g = 0, dp_n2b = 0, dp_pw = 0, dp_pb = 0, dp_cw = 0, dp_cb = 0, sdp_cw = 0, sdp_cb = 0,
          ea = 0;               // ea: {m[0], logs[0]} of sdp.flows.0
   DdsLayers dds[4];            // 0: sdp.convs, j = 1..3: sdp.flows.{2j+1}.convs (flows.1 is never run in reverse, models.py:172)
@@ -158,7 +153,10 @@ struct ovc_ctx {
   TcLayer tc_c1[12][3], tc_c2[12][3], tc_ups[4];
   float* d_tcw = nullptr;      // tensor-core weight arena (hi/lo split)
   std::vector<float> h_tcw;
-  int precision = 0;           // 0: fp32 FFMA everywhere; 1: 3xTF32 tcgen05 for the generator ResBlock convs
+  int precision = 0;           // 0: fp32 FFMA everywhere; 1: 3xFP16 split-precision tcgen05 convs; 2: single-pass fp16
+  int wide_variant = 0;        // tiling of the 128-column tensor-core kernel (see launch_tc)
+  bool tts_simple = false;     // OVC_OPT_TTS_SIMPLE
+  bool use_graph = true;       // OVC_OPT_GRAPH
   size_t post_w_off = 0;
   // cond mat-vec
   size_t cond_w_off = 0, cond_b_off = 0;
@@ -196,7 +194,7 @@ struct ovc_ctx {
   double prof_ms = 0, prof_flops = 0, prof_bytes = 0;
   int64_t prof_launches = 0;
   std::vector<double> ev_flops, ev_bytes;
-  std::vector<int> ev_variant, ev_family;
+  std::vector<int> ev_variant, ev_family, ev_tag;   // tag: (Cin << 16 | K << 8 | dilation) of a tensor-core launch, else 0
 
   // debug taps
   bool debug = false;
@@ -346,40 +344,31 @@ static int pack_wn(ovc_ctx* c, const std::string& prefix, int n_layers, WNLayers
   return 0;
 }
 
-// tensor-core copy of a conv: [n_tile][Cin/8][K][hi|lo][k chunk][TN][4], tf32-exact high part + fp32
-// remainder, laid out exactly as the kernel's shared-memory operand slots (one TMA bulk copy per slot)
+// tensor-core copy of a conv: fp16 [n_tile][Cin/16][K][hi|lo][column block][TN][8]: hi = fp16(w), lo = fp16((w - hi) * 2^11)
+// (ovc_tc.cuh), laid out exactly as the kernel's shared-memory operand slots (one TMA bulk copy per slot)
 template <class WF, class BF>
 static TcLayer pack_tc(ovc_ctx* c, int Ntot, int Cin, int K, int DIL, WF wfun, BF bfun) {
   TcLayer T;
   T.Cin = Cin; T.Ntot = Ntot; T.K = K; T.DIL = DIL;
   T.TN = Ntot % 128 == 0 ? 128 : (Ntot % 64 == 0 ? 64 : 32);   // widest column tile that divides the row
+  // the wide kernel stages 16 input channels at a time, the narrow ones 32; halo tile = 2 * 25 rows at most
+  if (Ntot % 32 || Cin % (T.TN == 128 ? 16 : 32) || (K - 1) / 2 * DIL > 25) { T.TN = 0; return T; }
   T.w_off = round_up(c->h_tcw.size(), 64);
-  const int slot = 2 * 2 * T.TN * 4;
-  c->h_tcw.resize(T.w_off + (size_t)(Ntot / T.TN) * (Cin / 8) * K * slot, 0.f);
-  float* dst = c->h_tcw.data() + T.w_off;
+  const int slot = 16 * T.TN;   // floats: 2 (hi|lo) x 2 (column blocks) x TN x 8 halfs
+  c->h_tcw.resize(T.w_off + (size_t)(Ntot / T.TN) * (Cin / 16) * K * slot, 0.f);
+  uint16_t* dst = reinterpret_cast<uint16_t*>(c->h_tcw.data() + T.w_off);
   for (int nt = 0; nt < Ntot / T.TN; ++nt)
-    for (int k8 = 0; k8 < Cin / 8; ++k8)
+    for (int k16 = 0; k16 < Cin / 16; ++k16)
       for (int tap = 0; tap < K; ++tap) {
-        float* sl = dst + (((size_t)nt * (Cin / 8) + k8) * K + tap) * slot;
+        uint16_t* sl = dst + (((size_t)nt * (Cin / 16) + k16) * K + tap) * (2 * slot);
         for (int kc = 0; kc < 2; ++kc)
           for (int n = 0; n < T.TN; ++n)
-            for (int e = 0; e < 4; ++e) {
-              const float w = wfun(nt * T.TN + n, k8 * 8 + kc * 4 + e, tap);
-              uint32_t bits;
-              memcpy(&bits, &w, 4);
-              bits &= 0xFFFFE000u;
-              float hi;
-              memcpy(&hi, &bits, 4);
-#if OVC_TC_PAIR
-              if (T.TN == 128) {   // pair layout: [rank][hi|lo][k chunk][64][4], CTA `rank` stages columns [64 * rank, +64)
-                const int rank = n / 64, nn = n % 64;
-                sl[(((rank * 2 + 0) * 2 + kc) * 64 + nn) * 4 + e] = hi;
-                sl[(((rank * 2 + 1) * 2 + kc) * 64 + nn) * 4 + e] = w - hi;
-                continue;
-              }
-#endif
-              sl[(kc * T.TN + n) * 4 + e] = hi;
-              sl[2 * T.TN * 4 + (kc * T.TN + n) * 4 + e] = w - hi;
+            for (int e = 0; e < 8; ++e) {
+              const float w = wfun(nt * T.TN + n, k16 * 16 + kc * 8 + e, tap);
+              const __half hi = __float2half_rn(w);
+              const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
+              sl[((0 * 2 + kc) * T.TN + n) * 8 + e] = __half_as_ushort(hi);
+              sl[((1 * 2 + kc) * T.TN + n) * 8 + e] = __half_as_ushort(lo);
             }
       }
   T.b_off = round_up(c->h_tcw.size(), 64);
@@ -643,12 +632,9 @@ static int finalize(ovc_ctx* c) {
   CK(cudaMemcpy(c->d_tcw, c->h_tcw.data(), c->h_tcw.size() * sizeof(float), cudaMemcpyHostToDevice));
   c->h_tcw.clear();
   c->h_tcw.shrink_to_fit();
-  CK(cudaFuncSetAttribute(tcconv_kernel<128, TC_CL128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<128>::SMEM_BYTES));
-#if OVC_TC_PAIR
-  CK(cudaFuncSetAttribute(tcconv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPairCfg::SMEM_BYTES));
-#endif
-  CK(cudaFuncSetAttribute(tcconv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<64>::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tcconv_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<32>::SMEM_BYTES));
+  CK((cudaFuncSetAttribute(tcconv_wide_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcwCfg<1, 2>::SMEM_BYTES)));
+  CK((cudaFuncSetAttribute(tcconv_wide_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcwCfg<1, 1>::SMEM_BYTES)));
+  CK((cudaFuncSetAttribute(tcconv_wide_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcwCfg<2, 1>::SMEM_BYTES)));
   CK(cudaFuncSetAttribute(tcconv_narrow_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<64>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tcconv_narrow_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<32>::SMEM_BYTES));
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
@@ -752,6 +738,7 @@ static int launch(Run& r, const ConvLayer& L, ConvArgs a, int t_len, bool mrf = 
     c->ev_bytes.push_back(4.0 * units * ((double)L.cin + (double)L.cout * L.out_mul));
     c->ev_variant.push_back(L.variant);
     c->ev_family.push_back(mrf ? 1 : 0);
+    c->ev_tag.push_back(0);
   }
   (void)flops; (void)bytes;
   return OVC_OK;
@@ -785,7 +772,7 @@ static int prof_begin(Run& r) {
   CK(cudaEventRecord(c->ev[c->ev_used], r.st));
   return OVC_OK;
 }
-static int prof_end(Run& r, int variant, int family, double flops, double bytes) {
+static int prof_end(Run& r, int variant, int family, double flops, double bytes, int tag = 0) {
   ovc_ctx* c = r.c;
   if (!c->prof) return OVC_OK;
   CK(cudaEventRecord(c->ev[c->ev_used + 1], r.st));
@@ -794,6 +781,7 @@ static int prof_end(Run& r, int variant, int family, double flops, double bytes)
   c->ev_bytes.push_back(bytes);
   c->ev_variant.push_back(variant);
   c->ev_family.push_back(family);
+  c->ev_tag.push_back(tag);
   return OVC_OK;
 }
 enum { V_TC128 = -1, V_TC64 = -2, V_TC32 = -3, V_TRANSPOSE = -4, V_TTS_DENSE = -5, V_TTS_LN = -6, V_TTS_SCORES = -7,
@@ -815,7 +803,7 @@ static const char* variant_name(int v) {
   }
 }
 
-// one conv on the tensor cores (3xTF32 / TF32), channels-last in/out.  t_len / mul are in INPUT steps.
+// one conv on the tensor cores (3xFP16 split precision / single-pass fp16), channels-last in/out.  t_len / mul are in INPUT steps.
 struct TcExtra {
   int epi = 0;                    // 0 linear, 1 WN gate, 2 WN res/skip
   const float* bias = nullptr;    // override (per-utterance conditioning vector), with stride
@@ -830,7 +818,7 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   TcConvArgs a{};
   const int y_ld = ex.y_ld ? ex.y_ld : T.Ntot;
   a.x = x; a.x_bs = (long long)T.Cin * r.P * mul;
-  a.w = r.c->d_tcw + T.w_off;
+  a.w = reinterpret_cast<const uint16_t*>(r.c->d_tcw + T.w_off);
   a.bias = ex.bias ? ex.bias : r.c->d_tcw + T.b_off; a.bias_bs = ex.bias_bs;
   a.y = y; a.y_bs = (long long)y_ld * r.P * mul; a.y_ld = y_ld;
   a.r = res;
@@ -840,46 +828,47 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   a.Cin = T.Cin; a.Ntot = T.Ntot; a.K = T.K; a.DIL = T.DIL;
   a.slope = slope; a.scale = scale; a.accumulate = accumulate;
   a.passes = r.c->precision == 2 ? 1 : 3;
-  {
-    const char* e = getenv("OVC_TC_DBG");   // timing ablations only (tools/layer_report.py --ablate)
-    a.dbg = e ? atoi(e) : 0;
-  }
-  const int steps = (T.TN == 128 ? TcCfg<128>::MT : TcCfg<64>::MT) * 128;
-  dim3 grid((t_len + steps - 1) / steps, T.Ntot / T.TN, r.B);
+  if (T.TN == 0) return fail(OVC_ERR_INVALID, "conv %d -> %d (k %d, dilation %d) does not fit the tensor-core kernels", T.Cin, T.Ntot, T.K, T.DIL);
   TRY(prof_begin(r));
-#if OVC_TC_PAIR
   if (T.TN == 128) {
-    grid.x = (grid.x + 1) / 2 * 2;                             // whole CTA pairs along time
-    tcconv_pair_kernel<<<grid, TC_THREADS, TcPairCfg::SMEM_BYTES, r.st>>>(a);
-  } else
-#endif
-  if (T.TN == 128) {
-    grid.x = (grid.x + TC_CL128 - 1) / TC_CL128 * TC_CL128;   // whole clusters along time
+    // wide_variant 0: 128-step tiles, two CTAs per SM, 2-CTA clusters multicasting the weight stream;
+    //              1: 256-step tiles, one CTA per SM; 2: as 0 without clusters
+    const int wv = r.c->wide_variant;
+    const int MT = wv == 1 ? 2 : 1, CL = wv == 0 ? 2 : 1;
+    dim3 grid((t_len + MT * 128 - 1) / (MT * 128), T.Ntot / 128, r.B);
+    grid.x = (grid.x + CL - 1) / CL * CL;   // whole clusters along time
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg<128>::SMEM_BYTES; cfg.stream = r.st;
+    cfg.gridDim = grid; cfg.stream = r.st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = TC_CL128; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, tcconv_kernel<128, TC_CL128>, a));
+    if (wv == 0) {
+      cfg.blockDim = dim3(TcwCfg<1, 2>::THREADS); cfg.dynamicSmemBytes = TcwCfg<1, 2>::SMEM_BYTES;
+      CK((cudaLaunchKernelEx(&cfg, tcconv_wide_kernel<1, 2>, a)));
+    } else if (wv == 1) {
+      cfg.blockDim = dim3(TcwCfg<2, 1>::THREADS); cfg.dynamicSmemBytes = TcwCfg<2, 1>::SMEM_BYTES;
+      CK((cudaLaunchKernelEx(&cfg, tcconv_wide_kernel<2, 1>, a)));
+    } else {
+      cfg.blockDim = dim3(TcwCfg<1, 1>::THREADS); cfg.dynamicSmemBytes = TcwCfg<1, 1>::SMEM_BYTES;
+      CK((cudaLaunchKernelEx(&cfg, tcconv_wide_kernel<1, 1>, a)));
+    }
   } else {
-    static const bool persistent = !(getenv("OVC_TC_NARROW") && atoi(getenv("OVC_TC_NARROW")) == 0);
-    if (persistent) {
-      // one CTA per SM walks the (utterance, 512-step tile) list; column tiles (if any) on grid.y
-      const int n_tt = (int)grid.x, total = n_tt * r.B;
-      const int per_col = std::max(1, r.c->sm_count / (int)grid.y);
-      dim3 pg((unsigned)std::min(total, per_col), grid.y, 1);
-      if (T.TN == 64) tcconv_narrow_kernel<64><<<pg, TCN_THREADS, TcnCfg<64>::SMEM_BYTES, r.st>>>(a, n_tt, total);
-      else tcconv_narrow_kernel<32><<<pg, TCN_THREADS, TcnCfg<32>::SMEM_BYTES, r.st>>>(a, n_tt, total);
-    } else if (T.TN == 64) tcconv_kernel<64, 1><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, r.st>>>(a);
-    else tcconv_kernel<32, 1><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, r.st>>>(a);
+    // one CTA per SM walks the (utterance, tile) list; column tiles (if any) on grid.y
+    const int steps = (T.TN == 64 ? TcnCfg<64>::MT : TcnCfg<32>::MT) * 128;
+    const int n_tt = (t_len + steps - 1) / steps, total = n_tt * r.B;
+    const int ncol = T.Ntot / T.TN;
+    const int per_col = std::max(1, r.c->sm_count / ncol);
+    dim3 pg((unsigned)std::min(total, per_col), ncol, 1);
+    if (T.TN == 64) tcconv_narrow_kernel<64><<<pg, TCN_THREADS, TcnCfg<64>::SMEM_BYTES, r.st>>>(a, n_tt, total);
+    else tcconv_narrow_kernel<32><<<pg, TCN_THREADS, TcnCfg<32>::SMEM_BYTES, r.st>>>(a, n_tt, total);
   }
   CK(cudaGetLastError());
   r.c->launches++;
   const double units = (double)r.B * t_len;
   const int eff_k = family == 2 ? 2 : T.K;   // polyphase transposed conv: 2 of the 3 packed taps are non-zero per row
   TRY(prof_end(r, T.TN == 128 ? V_TC128 : T.TN == 64 ? V_TC64 : V_TC32, family == 1 ? 1 : 0, 2.0 * T.Cin * T.Ntot * eff_k * units,
-               4.0 * (T.Cin + T.Ntot) * units));
+               4.0 * (T.Cin + T.Ntot) * units, (T.Cin << 16) | (T.K << 8) | T.DIL));
   return OVC_OK;
 }
 
@@ -1437,6 +1426,19 @@ int ovc_set_precision(ovc_ctx* c, int mode) {
   return OVC_OK;
 }
 
+int ovc_set_option(ovc_ctx* c, int key, int value) {
+  if (!c) return fail(OVC_ERR_INVALID, "null context");
+  switch (key) {
+    case OVC_OPT_WIDE_VARIANT:
+      if (value < 0 || value > 2) return fail(OVC_ERR_INVALID, "wide variant must be 0, 1 or 2");
+      c->wide_variant = value;
+      return OVC_OK;
+    case OVC_OPT_TTS_SIMPLE: c->tts_simple = value != 0; return OVC_OK;
+    case OVC_OPT_GRAPH: c->use_graph = value != 0; return OVC_OK;
+    default: return fail(OVC_ERR_INVALID, "unknown option %d", key);
+  }
+}
+
 int ovc_last_launch_count(const ovc_ctx* c) { return c ? c->launches : 0; }
 
 int ovc_profile_enable(ovc_ctx* c, int enable) {
@@ -1447,6 +1449,7 @@ int ovc_profile_enable(ovc_ctx* c, int enable) {
   c->ev_bytes.clear();
   c->ev_variant.clear();
   c->ev_family.clear();
+  c->ev_tag.clear();
   return OVC_OK;
 }
 
@@ -1472,6 +1475,7 @@ int ovc_profile_read(ovc_ctx* c, double* ms, int64_t* launches, double* flops, d
   c->ev_bytes.clear();
   c->ev_variant.clear();
   c->ev_family.clear();
+  c->ev_tag.clear();
   return OVC_OK;
 }
 
@@ -1481,7 +1485,11 @@ int ovc_profile_detail(ovc_ctx* c, int max, char* names /* max x 16 */, double* 
   for (size_t i = 0; i + 1 < c->ev_used && n < max; i += 2, ++n) {
     float m = 0;
     CK(cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]));
-    if (names) { strncpy(names + 16 * n, variant_name(c->ev_variant[i / 2]), 15); names[16 * n + 15] = 0; }
+    if (names) {
+      const int tag = c->ev_tag[i / 2], v = c->ev_variant[i / 2];
+      if (tag) snprintf(names + 16 * n, 16, "T%dc%dk%dd%d", v == V_TC128 ? 128 : v == V_TC64 ? 64 : 32, tag >> 16, (tag >> 8) & 255, tag & 255);
+      else { strncpy(names + 16 * n, variant_name(v), 15); names[16 * n + 15] = 0; }
+    }
     if (ms) ms[n] = m;
     if (flops) flops[n] = c->ev_flops[i / 2];
     if (bytes) bytes[n] = c->ev_bytes[i / 2];

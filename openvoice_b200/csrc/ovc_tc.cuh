@@ -1,9 +1,11 @@
 // ovc_tc.cuh -- tcgen05 / TMEM helpers (sm_100a inline PTX) for the split-precision tensor-core
 // convolution path.  Operand layout used everywhere: K-major, no swizzle ("interleave"):
-//   address(row, k) = base + (k / 4) * LBO + (row / 8) * SBO + (row % 8) * 16 + (k % 4) * 4     [tf32 / fp32]
-// with SBO = 128 bytes, i.e. rows are uniformly 16 bytes apart inside one 4-channel column
+//   address(row, k) = base + (k / 8) * LBO + (row / 8) * SBO + (row % 8) * 16 + (k % 8) * 2     [f16]
+// with SBO = 128 bytes, i.e. rows are uniformly 16 bytes apart inside one 8-channel column
 // block, so a convolution tap is just a start-address shift of (tap offset) * 16 bytes.
+// One tcgen05.mma.kind::f16 covers K = 16 channels = two column blocks (LBO apart).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,6 +23,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, K-major A and B
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// ... for kind::f16 with fp16 A and B (a_format = b_format = 0), fp32 accumulate (c_format = 1), K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // one full warp
@@ -40,6 +46,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T with fp16 operands (K = 16 per instruction), fp32 accumulation
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
@@ -102,6 +117,32 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = x - hi;
+}
+
+// ---- split precision on fp16 operands ("3xFP16"):  x = hi + lo / 2^11 (+ 2^-23 |x|), hi = fp16(x),
+// lo = fp16((x - hi) * 2^11).  The remainder is scaled back into fp16's normal range, so the pair carries 22
+// mantissa bits for any |x| < 65504 (absolute floor 2^-36); a*b ~ ah*bh + (al*bh + ah*bl) / 2^11, the two cross
+// terms accumulate in their own TMEM accumulator and the epilogue adds them with the 2^-11 factor.  fp16 MMAs run
+// at twice the TF32 rate and move half the operand bytes, at the same 11-bit-per-part precision as 3xTF32.
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+
+// 8 consecutive channels of one row (after the input leaky-relu) -> 16 bytes of hi parts + 16 bytes of lo parts
+__device__ __forceinline__ void split_f16x8(float4 a, float4 b, float slope, uint4& hi, uint4& lo) {
+  float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x0 = x[2 * i], x1 = x[2 * i + 1];
+    x0 = x0 > 0.f ? x0 : x0 * slope;
+    x1 = x1 > 0.f ? x1 : x1 * slope;
+    const __half2 hh = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn((x0 - hf.x) * kLoScale, (x1 - hf.y) * kLoScale);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 }  // namespace tc

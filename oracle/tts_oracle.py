@@ -202,7 +202,7 @@ def rel_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: torch
     scores = scores.masked_fill(pair == 0, -1e4)
     p = torch.softmax(scores, dim=-1)
     out = p @ vh
-    pw = torch.zeros(B, n_heads, T, 2 * window + 1)
+    pw = torch.zeros(B, n_heads, T, 2 * window + 1, dtype=p.dtype)
     pw.scatter_add_(3, slot[None, None].expand(B, n_heads, T, T), p * inside)
     out = out + pw @ rel_v[0]
     return out.transpose(2, 3).reshape(B, C, T)

@@ -31,7 +31,7 @@ _native_cache = {}
 def pytest_generate_tests(metafunc):
     # every GPU parity test that takes `native` runs in both arithmetic modes of the generator
     if "native" in metafunc.fixturenames:
-        metafunc.parametrize("native", ["fp32", "tf32x3"], indirect=True)
+        metafunc.parametrize("native", ["fp32", "f16x3"], indirect=True)
 
 
 def get_native(zero_g=False):

@@ -120,6 +120,58 @@ def test_flow_roundtrip_property_full_size(native):
     assert o.shape == (B, 1, 256 * T)
 
 
+def _oracle_solo(sd, spec, lengths, gs, gt, noise, b, tau, zero_g=False):
+    L = int(lengths[b])
+    with torch.no_grad():
+        return O.voice_conversion(sd, spec[b:b + 1, :, :L].contiguous(), lengths[b:b + 1], gs[b:b + 1], gt[b:b + 1],
+                                  noise[b:b + 1, :, :L].contiguous(), tau, zero_g)
+
+
+def test_benched_config_vs_oracle(native, synthetic_sd):
+    """The BENCHED configuration (BASELINE configs[1]: 32 x 10 s clips, T = 861, ragged = convert semantics) against
+    the CPU oracle: two full-length clips and one shorter clip taken out of the batch of 32, every tensor of
+    voice_conversion (models.py:492-499) within the stated 1e-4 * rms, in both arithmetic modes."""
+    B, T = 32, 861
+    lens = [T] * B
+    lens[5], lens[17] = 640, 258
+    spec, lengths, gs, gt, noise = O.synthetic_inputs(B, T, 861, lengths=lens)
+    o, mask, (z, zp, zh) = run_native(native, spec, lengths, gs, gt, noise, 0.3, ragged=True)
+    assert o.shape == (B, 1, 256 * T)
+    worst = {}
+    for b in (0, 31, 5):
+        L = lens[b]
+        ro, _, (rz, rzp, rzh) = _oracle_solo(synthetic_sd, spec, lengths, gs, gt, noise, b, 0.3)
+        for k, got, ref in (("z", z[b, :, :L], rz[0]), ("z_p", zp[b, :, :L], rzp[0]), ("z_hat", zh[b, :, :L], rzh[0]),
+                            ("o_hat", o[b, 0, : 256 * L], ro[0, 0])):
+            e = rel_err(got.numpy(), ref.numpy())
+            worst[k] = max(worst.get(k, 0.0), e)
+            assert e <= REL, (b, k, e)
+        assert float(o[b, 0, 256 * L:].abs().max()) == 0.0 if L < T else True
+    print("benched-config parity (max over 3 clips):", worst)
+
+
+def test_thirty_second_clip_vs_oracle(native, synthetic_sd):
+    """One 30 s clip (T = 2583, BASELINE configs[4]'s longest) against the oracle."""
+    T = 2583
+    spec, lengths, gs, gt, noise = O.synthetic_inputs(1, T, 2583)
+    o, _, (z, zp, zh) = run_native(native, spec, lengths, gs, gt, noise, 0.3, ragged=True)
+    ro, _, (rz, rzp, rzh) = _oracle_solo(synthetic_sd, spec, lengths, gs, gt, noise, 0, 0.3)
+    for k, got, ref in (("z", z, rz), ("z_p", zp, rzp), ("z_hat", zh, rzh), ("o_hat", o, ro)):
+        assert rel_err(got.numpy(), ref.numpy()) <= REL, k
+
+
+def test_v2_zero_g_full_size_vs_oracle(native_v2, synthetic_sd):
+    """V2 converter semantics (zero_g, models.py:495,498) at T = 861 (BASELINE configs[3] clip size), default mode."""
+    T = 861
+    spec, lengths, gs, gt, noise = O.synthetic_inputs(2, T, 8612, lengths=[T, 700])
+    o, _, (z, zp, zh) = run_native(native_v2, spec, lengths, gs, gt, noise, 0.3, ragged=True)
+    for b, L in ((0, T), (1, 700)):
+        ro, _, (rz, rzp, rzh) = _oracle_solo(synthetic_sd, spec, lengths, gs, gt, noise, b, 0.3, zero_g=True)
+        for k, got, ref in (("z", z[b, :, :L], rz[0]), ("z_p", zp[b, :, :L], rzp[0]), ("z_hat", zh[b, :, :L], rzh[0]),
+                            ("o_hat", o[b, 0, : 256 * L], ro[0, 0])):
+            assert rel_err(got.numpy(), ref.numpy()) <= REL, (b, k)
+
+
 def test_in_kernel_noise_statistics(native):
     """noise=None draws Philox normals in-kernel: (z - m)/(tau*exp(logs)) must look N(0,1) and be
     reproducible from the seed.  tau=0 run gives m; a second tau gives the scaled noise."""
@@ -138,23 +190,23 @@ def test_in_kernel_noise_statistics(native):
     assert abs(float((eps ** 3).mean())) < 0.05 and abs(float((eps ** 4).mean()) - 3.0) < 0.15
 
 
-def test_single_pass_tf32_mode_has_its_own_gate(synthetic_sd):
-    """precision="tf32" = one TF32 pass per conv on the tensor cores -- what the reference itself runs on a GPU
-    (cuDNN allow_tf32 defaults to True).  Stated gate for this mode: waveform SNR >= 30 dB against the fp32
-    oracle and latents within 2e-2 * rms; the default modes are held to 1e-4 * rms elsewhere in this file."""
+def test_single_pass_f16_mode_has_its_own_gate(synthetic_sd):
+    """precision="f16" = one fp16 pass per conv on the tensor cores: 11-bit operands, the precision class the reference
+    itself runs on a GPU (cuDNN allow_tf32 defaults to True).  Stated gate for this mode: waveform SNR >= 30 dB against
+    the fp32 oracle and latents within 2e-2 * rms; the default modes are held to 1e-4 * rms elsewhere in this file."""
     from conftest import get_native
     m = get_native(False)
     spec, lengths, gs, gt, noise = O.synthetic_inputs(2, 90, 21, lengths=[90, 57])
     with torch.no_grad():
         ro, _, (rz, rzp, rzh) = O.voice_conversion(synthetic_sd, spec, lengths, gs, gt, noise, 0.3)
-    m.native.set_precision("tf32")
+    m.native.set_precision("f16")
     try:
         o, _, (z, zp, zh) = run_native(m, spec, lengths, gs, gt, noise, 0.3)
     finally:
         m.native.set_precision(m.precision)
     err = (o - ro).double()
     snr = 10 * np.log10(float(ro.double().pow(2).mean() / err.pow(2).mean()))
-    print("tf32 single-pass SNR dB:", snr, "z_hat rel", rel_err(zh.numpy(), rzh.numpy()))
+    print("f16 single-pass SNR dB:", snr, "z_hat rel", rel_err(zh.numpy(), rzh.numpy()))
     assert snr >= 30.0
     assert rel_err(zh.numpy(), rzh.numpy()) <= 2e-2
 
@@ -266,7 +318,7 @@ def test_time_tiled_long_clip_equals_whole_clip(tmp_path, synthetic_sd):
     src = 0.1 * torch.randn(1, 256, 1, generator=gen)
     tgt = 0.1 * torch.randn(1, 256, 1, generator=gen)
     noise = torch.randn(192, T, generator=gen)
-    for precision in ("fp32", "tf32x3"):
+    for precision in ("fp32", "f16x3"):
         conv = ToneColorConverter(str(cfg), device="cuda:0", enable_watermark=False, precision=precision)
         conv.model.load_state_dict(synthetic_sd)
         whole = conv.convert(wav, src, tgt, tau=0.3, noise=noise[None])

@@ -231,14 +231,3 @@ def test_base_speaker_host_helpers():
     assert a.dtype == np.float32 and len(a) == 10 + 4 + 2 * gap
     assert a[:10].tolist() == [1.0] * 10 and a[10:10 + gap].tolist() == [0.0] * gap and a[10 + gap:14 + gap].tolist() == [2.0] * 4
     assert BaseSpeakerTTS.language_marks == {"english": "EN", "chinese": "ZH"}
-
-
-def test_pair_kernel_barrier_protocol_model():
-    """The barrier protocol of the (not yet enabled) CTA-pair tcconv kernel, randomised interleavings on a small ring:
-    no deadlock, no slot / buffer overwritten under a reader, no MMA on operands that have not landed in both CTAs."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("pair_protocol_sim", os.path.join(ROOT, "tools", "pair_protocol_sim.py"))
-    sim = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(sim)
-    for seed in range(400):
-        sim.run(seed)

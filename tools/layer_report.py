@@ -20,8 +20,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--secs", type=float, default=10.0)
     ap.add_argument("--json", default=None)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
-    ap.add_argument("--ablate", default="", help="comma list of OVC_TC_DBG masks to time (1 producers, 2 epilogue, 4 MMAs off)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "f16x3", "f16"])
+    ap.add_argument("--wide-variant", type=int, default=None)
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -39,23 +39,11 @@ def main():
     g = 0.1 * torch.randn(B, 256, generator=torch.Generator().manual_seed(1)).cuda()
     nat = conv.model.native
     nat.set_precision(args.precision)
+    if args.wide_variant is not None:
+        nat.set_option("wide_variant", args.wide_variant)
     for _ in range(2):
         nat.convert_waveform(wav, wlen, g, g, tau=0.3, seed=1)
     torch.cuda.synchronize()
-    for mask in [m for m in args.ablate.split(",") if m]:
-        os.environ["OVC_TC_DBG"] = mask
-        nat.convert_waveform(wav, wlen, g, g, tau=0.3, seed=1)
-        torch.cuda.synchronize()
-        nat.profile_enable(True)
-        nat.convert_waveform(wav, wlen, g, g, tau=0.3, seed=2)
-        torch.cuda.synchronize()
-        agg = collections.OrderedDict()
-        for name, ms, fl, by, fam in nat.profile_detail():
-            agg[name] = agg.get(name, 0.0) + ms
-        nat.profile_read()
-        nat.profile_enable(False)
-        print(f"ablate mask {mask}: " + "  ".join(f"{k}={v:.2f}ms" for k, v in agg.items() if k.startswith("TC")))
-    os.environ["OVC_TC_DBG"] = "0"
     nat.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -25,7 +25,7 @@ spec, lengths, gs, gt, noise = O.synthetic_inputs(B, T, 3, lengths=lens)
 taps = {}
 with torch.no_grad():
     ro, _, (rz, rzp, rzh) = O.voice_conversion(sd, spec, lengths, gs, gt, noise, 0.3, taps=taps)
-for mode in ("fp32", "tf32x3", "tf32"):
+for mode in ("fp32", "f16x3", "f16"):
     m.native.set_precision(mode)
     m.native.debug_enable(True)
     o, _, lat = m.voice_conversion(spec.cuda(), lengths.cuda(), gs.cuda(), gt.cuda(), tau=0.3, noise=noise.cuda(), ragged=False)

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def measure(batch=16, tokens=121, iters=5, cpu=False, precision="tf32x3"):
+def measure(batch=16, tokens=121, iters=5, cpu=False, precision="f16x3"):
     a = argparse.Namespace(batch=batch, tokens=tokens, iters=iters, cpu=cpu, precision=precision)
 
     from oracle import tts_oracle as T          # synthetic checkpoint recipe + the optional CPU leg only
@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=121)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on one sentence (test infrastructure)")
-    ap.add_argument("--precision", default="tf32x3")
+    ap.add_argument("--precision", default="f16x3")
     a = ap.parse_args()
     print(json.dumps(measure(a.batch, a.tokens, a.iters, a.cpu, a.precision)))
 
