@@ -13,11 +13,15 @@ broadcasts the checkpoint and, in the end-to-end leg, gathers the output wavefor
 
 One JSON line on stdout (rank 0):
   value      device-resident: waveforms already in HBM -> ovc_convert_waveform (STFT + voice_conversion), CUDA events
-  e2e        through ToneColorConverter.convert_batch with HOST numpy waveforms: pinned H2D, STFT,
-             voice_conversion, D2H of the samples, all inside the timed region
-  roofline   generator ResBlock conv family (90 % of the FLOPs): algorithmic layer-granular bytes
-             / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs, plus the fp32 FFMA numbers that
-             actually bind
+  e2e        HOST numpy waveforms in, HOST numpy waveforms out, all inside the timed region: N = 1 through
+             ToneColorConverter.convert_batch (pinned H2D, kernels, D2H); N > 1 through
+             openvoice_b200.distributed.convert_sharded_async (each rank uploads and converts its shard, the
+             results are gathered GPU-to-GPU over NCCL and downloaded on rank 0; one call in flight behind the
+             current one, so a step's gather + download overlap the next step's kernels)
+  roofline   generator ResBlock conv family (90 % of the FLOPs), timed live with CUDA events around every launch:
+             ALGORITHMIC TFLOP/s (2*MAC of the reference's convs, no credit for the 3 split-precision passes) over
+             the measured dense fp16/bf16 tensor peak; pipe occupancy, HBM figures and a per-kernel table beside it
+  cudnn_baseline  the reference's own torch graph (oracle port, F.conv1d -> cuDNN) on this GPU, TF32 on and off
   cpu_baseline  the oracle port of the reference's CPU path on this box's host cores (N=1 only)
 --impl reference times that CPU path alone (the reference arm).
 """
@@ -189,6 +193,74 @@ def quiet_stdout():
     os.dup2(2, 1)
 
 
+def cudnn_reference(B, secs, steps=3):
+    """SURVEY section 8d's third column: the reference's own PyTorch graph on THIS GPU (cuDNN convolutions; the oracle
+    port issues the same F.conv1d / conv_transpose1d calls as openvoice/models.py), batch B x secs padded batch,
+    explicit noise, TF32 on (torch's cudnn default) and off.  Never part of the product path."""
+    import torch
+    from oracle import vc_oracle as O
+    dev = "cuda"
+    sd = {k: v.to(dev) for k, v in O.synthetic_state_dict(1234).items()}
+    wav = torch.from_numpy(np.stack([synth_wave(i, secs) for i in range(B)])).to(dev)
+    T = wav.shape[1] // HOP
+    gs = torch.cat([synth_se(i, 2000) for i in range(B)]).to(dev)
+    gt = torch.cat([synth_se(i, 3000) for i in range(B)]).to(dev)
+    lengths = torch.full((B,), T, dtype=torch.int64, device=dev)
+    noise = torch.randn(B, 192, T, device=dev)
+    out = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
+            def step():
+                with torch.no_grad():
+                    spec = O.spectrogram(wav)
+                    return O.voice_conversion(sd, spec, lengths, gs, gt, noise, 0.3)[0]
+            step(); step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                o = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out["tf32_on" if tf32 else "tf32_off"] = {"audio_s_per_s": B * T * HOP / SR / (ms * 1e-3), "ms_per_step": ms}
+            del o
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+        torch.cuda.empty_cache()
+    out["what"] = (f"oracle port of the reference graph (F.conv1d -> cuDNN, weight-norm folded every call like the reference), "
+                   f"padded batch {B} x {secs:g} s, torch {torch.__version__}, cudnn.benchmark on, CUDA events, {steps} steps")
+    return out
+
+
+def latency_config1(conv, secs_list=(3.0, 10.0), iters=20):
+    """BASELINE configs[0] on the GPU: ToneColorConverter.convert of ONE clip (batch 1), host array in, host array
+    out, median wall time."""
+    import torch
+    out = {}
+    src, tgt = synth_se(0, 2000), synth_se(0, 3000)
+    for secs in secs_list:
+        w = synth_wave(0, secs)
+        for _ in range(3):
+            conv.convert(w, src, tgt, tau=0.3)
+        ts = []
+        for _ in range(iters):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            conv.convert(w, src, tgt, tau=0.3)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ms = float(np.median(ts))
+        out[f"{secs:g}s"] = {"ms": ms, "audio_s_per_s": (len(w) // HOP * HOP / SR) / (ms * 1e-3),
+                             "launches": int(conv.model.native.last_launch_count)}
+    out["what"] = "ToneColorConverter.convert, batch 1, host numpy in/out, median of %d wall-clock calls" % iters
+    return out
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -207,13 +279,18 @@ def main():
     ap.add_argument("--wide-variant", type=int, default=None, help="tiling of the 128-column tensor-core kernel (ovc_set_option)")
     ap.add_argument("--no-config3", action="store_true", help="skip the BASELINE config-3 side measurement (V1 TTS + convert, batch 16)")
     ap.add_argument("--no-modes", action="store_true", help="skip the short side measurements of the other precisions")
+    ap.add_argument("--no-cudnn", action="store_true", help="skip the reference-on-this-GPU (PyTorch / cuDNN) column")
+    ap.add_argument("--no-sides", action="store_true", help="skip every side measurement (modes, config1/3/4, cudnn, cpu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.no_sides:
+        args.no_config3 = args.no_modes = args.no_cudnn = args.no_cpu_baseline = True
 
     import torch
     import torch.distributed as dist
-    from oracle import vc_oracle as O          # synthetic checkpoint recipe + cpu_baseline only
+    from oracle import vc_oracle as O          # synthetic checkpoint recipe + cpu_baseline / cudnn_baseline only
+    from openvoice_b200 import distributed as D
     from openvoice_b200.api import ToneColorConverter
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,28 +304,22 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun"
 
     # ---- model: rank 0 owns the checkpoint, NCCL broadcasts it (north_star)
-    schema = O.state_dict_schema()
-    names = sorted(schema)
-    sizes = [int(np.prod(schema[k])) for k in names]
-    if rank == 0:
-        sd = O.synthetic_state_dict(1234)
-        flat = torch.cat([sd[k].reshape(-1) for k in names]).to(dev)
-    else:
-        flat = torch.empty(sum(sizes), device=dev)
-    if world > 1:
-        dist.broadcast(flat, 0)
-    parts = torch.split(flat.cpu(), sizes)
-    sd = {k: p.reshape(schema[k]) for k, p in zip(names, parts)}
-    del flat
-    with tempfile.TemporaryDirectory() as td:
-        cfg = os.path.join(td, "config.json")
-        json.dump(O.DEFAULT_HPARAMS, open(cfg, "w"))
-        conv = ToneColorConverter(cfg, device=dev, enable_watermark=False, precision=args.precision)
-    conv.model.load_state_dict(sd)
-    del sd
-    if args.wide_variant is not None:
-        conv.model.native.set_option("wide_variant", args.wide_variant)
+    sd = D.broadcast_state_dict(O.synthetic_state_dict(1234) if rank == 0 else None, device=dev)
 
+    def make_converter(zero_g=False):
+        import copy
+        hp = copy.deepcopy(O.DEFAULT_HPARAMS)
+        hp["model"]["zero_g"] = zero_g
+        with tempfile.TemporaryDirectory() as td:
+            cfg = os.path.join(td, "config.json")
+            json.dump(hp, open(cfg, "w"))
+            cv = ToneColorConverter(cfg, device=dev, enable_watermark=False, precision=args.precision)
+        cv.model.load_state_dict(sd)
+        if args.wide_variant is not None:
+            cv.model.native.set_option("wide_variant", args.wide_variant)
+        return cv
+
+    conv = make_converter()
     B, secs = args.batch, args.secs
     waves = [synth_wave(rank * B + i, secs) for i in range(B)]
     L = len(waves[0])
@@ -279,7 +350,6 @@ def main():
     for s in range(args.warmup):
         device_step(s)
     native = conv.model.native
-    native.profile_enable(True)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -291,9 +361,20 @@ def main():
     e1.record()
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches_per_call = native.last_launch_count
+
+    # ---- per-kernel leg (roofline): the same steps again with CUDA events around every conv launch
+    native.profile_enable(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for s in range(args.steps):
+        device_step(2000 + s)
+    p1.record()
+    torch.cuda.synchronize()
+    ms_prof_step = p0.elapsed_time(p1) / args.steps
+    detail = native.profile_detail(1 << 16)
     prof = native.profile_read()
     native.profile_enable(False)
-    launches_per_call = native.last_launch_count
 
     # ---- the other arithmetic modes, short (2 timed steps), device-resident only
     modes = {}
@@ -313,28 +394,76 @@ def main():
         native.set_precision(args.precision)
 
     # ---- end-to-end leg: host numpy in, host numpy out, through the public API
-    def e2e_step():
-        res = conv.convert_batch(waves, src, tgt, tau=0.3, max_batch=B)
-        if world > 1:   # gather the waveforms on rank 0 over NCCL
-            mine = torch.from_numpy(np.stack(res)).to(dev)
-            bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-            dist.gather(mine, bucket, dst=0)
-        return res
+    if world == 1:
+        def e2e_run(n):
+            res = None
+            for _ in range(n):
+                res = conv.convert_batch(waves, src, tgt, tau=0.3, max_batch=B)
+            return res
+        h2d, d2h = int(B * L * 4 + B * 8), int(B * T * HOP * 4)
+        e2e_api = "ToneColorConverter.convert_batch"
+    else:
+        # every rank holds the global utterance list (world * B clips); LPT sharding gives each rank B of them
+        all_waves = [synth_wave(i, secs) for i in range(world * B)]
+        all_src = [synth_se(i, 2000) for i in range(world * B)]
+        all_tgt = [synth_se(i, 3000) for i in range(world * B)]
 
-    for s in range(args.warmup):
-        e2e_step()
+        def e2e_run(n):
+            res, prev = None, None
+            for _ in range(n):
+                job = D.convert_sharded_async(conv, all_waves, all_src, all_tgt, tau=0.3)
+                if prev is not None:
+                    res = prev.result()      # step i's waveforms are on the host while step i+1 computes
+                prev = job
+            res = prev.result()
+            return res
+        h2d, d2h = int(B * L * 4 + B * 8), int(world * B * T * HOP * 4)
+        e2e_api = "openvoice_b200.distributed.convert_sharded_async (one call in flight; d2h on rank 0 only)"
+
+    e2e_run(args.warmup)
     barrier()
     t0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for s in range(args.steps):
-        res = e2e_step()
+    res = e2e_run(args.steps)
     g1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     ms_e2e = max_over_ranks(max(g0.elapsed_time(g1), wall_ms)) / args.steps
     clocks = sampler.stop() if rank == 0 else None
-    assert res[0].shape[0] == T * HOP and np.isfinite(res[0]).all()
+    if rank == 0:
+        assert len(res) == world * B and res[0].shape[0] == T * HOP and np.isfinite(res[0]).all() and np.isfinite(res[-1]).all()
+
+    # ---- config 4 (V2 converter: zero_g, 16 clips of 10 s per GPU, sharded): side key
+    config4 = None
+    if not args.no_sides:
+        try:
+            conv4 = make_converter(zero_g=True)
+            n4 = 16 * world
+            w4 = [synth_wave(5000 + i, 10.0) for i in range(n4)]
+            s4 = [synth_se(5000 + i, 2000) for i in range(n4)]
+            t4 = [synth_se(5000 + i, 3000) for i in range(n4)]
+
+            def run4(n):
+                prev, out = None, None
+                for _ in range(n):
+                    job = D.convert_sharded_async(conv4, w4, s4, t4, tau=0.3)
+                    if prev is not None:
+                        out = prev.result()
+                    prev = job
+                return prev.result()
+            run4(2)
+            barrier()
+            c0 = time.perf_counter()
+            r4 = run4(3)
+            barrier()
+            ms4 = max_over_ranks((time.perf_counter() - c0) * 1e3) / 3
+            a4 = n4 * (len(w4[0]) // HOP * HOP) / SR
+            config4 = {"workload": f"V2 converter (zero_g), global batch {n4} = 16 x 10 s per GPU, convert_sharded_async, host in / host out",
+                       "ms_per_step": ms4, "audio_s_per_s": a4 / (ms4 * 1e-3)}
+            del conv4
+        except Exception as e:      # a side measurement must never cost the headline line
+            config4 = {"error": f"{type(e).__name__}: {e}"[:240]}
 
     if rank != 0:
         if world > 1:
@@ -351,47 +480,64 @@ def main():
     k_ms = prof["ms"] / max(1, prof["launches"])
     ach_gbs = prof["bytes"] / max(1e-9, prof["ms"] * 1e-3) / 1e9
     ach_tf = prof["flops"] / max(1e-9, prof["ms"] * 1e-3) / 1e12
-    traffic, traffic_note = None, None
-    try:   # dram bytes of the top kernel from the committed ncu --set full capture (profiles/)
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_A_K11D1_ffma2.json")))[0]
-        traffic = (float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])) * 1e6
-        traffic_note = ("ncu dram read+write of one conv1d_f32<11,1,4,2,4> launch at batch 8 (C=128, 440832 steps): "
-                        "algorithmic in+out+residual = 677 MB")
-    except Exception:
-        pass
+
+    # per-kernel table of the generator ResBlock family (family flag 1): name -> [launches, ms, flops, bytes]
+    fam = {}
+    for name, ms, fl, by, f in detail:
+        if not f:
+            continue
+        key = {"T128": "tcconv_wide_kernel (C >= 128)", "T64c": "tcconv_narrow_kernel<64> (C = 64)",
+               "T32c": "tcconv_narrow_kernel<32> (C = 32)"}.get(name[:4], "conv1d_f32 (CUDA cores)")
+        a = fam.setdefault(key, [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
+
+    def ncu_traffic(pattern):
+        """dram read + write bytes of one launch of the dominant kernel from the committed ncu --set full capture"""
+        import glob
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", pattern))):
+            try:
+                cap = json.load(open(path))
+                cap = cap[0] if isinstance(cap, list) else cap
+                rd, wr = cap["dram__bytes_read.sum"].split(), cap["dram__bytes_write.sum"].split()
+                unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                return ((float(rd[0]) * unit.get(rd[1], 1.0) + float(wr[0]) * unit.get(wr[1], 1.0)),
+                        f"{os.path.basename(path)}: {cap.get('what', 'ncu --set full, one launch')}")
+            except Exception:
+                continue
+        return None, None
+
     if args.precision == "fp32":
+        traffic, traffic_note = ncu_traffic("r0*_ncu_full_A_K11D1_ffma2.json")
         roofline = {
             "kernel": "conv1d_f32<EPI_LINEAR> (generator ResBlock1 convs, 72 launches per call)",
             "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
             "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-            "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_dev,
+            "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_prof_step,
             "binding": "fp32 FFMA (dense contraction, SURVEY.md section 8d)",
             "ffma": {"achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FFMA_PEAK_TFLOPS,
                      "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"},
         }
     else:
-        # tensor-core modes: the MMA rate is what binds.  TF32 runs at half the bf16 rate; every algorithmic FLOP
-        # costs 3 tensor FLOPs in the split-precision mode.
+        # tensor-core modes.  achieved = ALGORITHMIC FLOPs (2*MAC of the reference's convs) / CUDA-event time; the split
+        # precision spends 3 tensor FLOPs per algorithmic FLOP, which shows up as pipe_occupancy, not as achieved work.
         passes = 3 if args.precision == "f16x3" else 1
-        tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
-        tc_traffic, tc_note = None, None
-        try:   # dram bytes of a representative launch of this kernel from the committed ncu --set full capture
-            caps = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_tcconv128_mrf_c256_c128_before_issue_fix.json")))
-            cap = [c for c in caps if c.get("launch__grid_size") == "1728"][1]
-            tc_traffic = (float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])) * 1e6
-            tc_note = ("ncu dram read+write of ONE tcconv_kernel<128> launch (C=128 ResBlock conv, batch 8 x 861 frames, "
-                       "55104 steps): algorithmic in + out = 451 MB; per-launch figure at another batch size, not this step's")
-        except Exception:
-            pass
+        tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        traffic, traffic_note = ncu_traffic("r02_ncu_full_wide_*.json")
         roofline = {
-            "kernel": "tcconv_kernel<TN> (generator ResBlock1 convs on tcgen05, 72 launches per call)",
-            "bound": "tensor", "achieved": ach_tf * passes, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": ach_tf * passes / tf32_peak, "traffic": tc_traffic, "traffic_note": tc_note,
-            "peak_source": ("measured" if "bf16_tflops_sustained" in peaks else "fallback") + " bf16 sustained / 2 (TF32 rate)",
-            "algorithmic_tflops": ach_tf, "mma_passes": passes,
-            "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_dev,
-            "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src},
+            "kernel": "tcconv_wide_kernel + tcconv_narrow_kernel (generator ResBlock1 convs on tcgen05, 72 launches per call)",
+            "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach_tf / tc_peak,
+            "frac_note": "algorithmic FLOPs / time / measured dense 16-bit tensor peak; the fp32-grade split precision needs "
+                         "3 MMA passes, so 1/3 is the ceiling of this mode",
+            "mma_passes": passes, "pipe_occupancy": ach_tf * passes / tc_peak,
+            "traffic": traffic, "traffic_note": traffic_note,
+            "peak_source": ("measured" if "bf16_tflops_sustained" in peaks else "fallback") + " dense bf16/fp16 sustained (MEASURED_PEAKS.json)",
+            "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_prof_step,
+            "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
+                    "note": "layer-granular algorithmic bytes (SURVEY 8d tier T2: in + out per conv) / time"},
         }
+    roofline["kernels"] = {
+        k: {"launches_per_step": a[0] // args.steps, "ms_per_step": a[1] / args.steps, "algorithmic_tflops": a[2] / a[1] / 1e9,
+            "algorithmic_gbs": a[3] / a[1] / 1e6} for k, a in sorted(fam.items(), key=lambda kv: -kv[1][1])}
     value = world * audio_s_step / (ms_dev * 1e-3)
     e2e_val = world * audio_s_step / (ms_e2e * 1e-3)
     line = {
@@ -404,14 +550,26 @@ def main():
                                "(BASELINE configs[1]), seeded synthetic checkpoint, tau 0.3, in-kernel Philox noise",
                    "batch_per_gpu": B, "global_batch": B * world, "secs": secs, "frames": T,
                    "l2": "activations per step (>3 GB) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": f"replicas x{world}"},
+                   "parallelism": f"replicas x{world}", "e2e_api": e2e_api},
         "tflops_algorithmic": world * B * T * GFLOP_PER_FRAME / ms_dev,
         "e2e": {"value": e2e_val, "unit": "audio-s/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(B * L * 4 + B * 8), "d2h_bytes_per_step": int(B * T * HOP * 4)},
-        "gpu_launches": int(launches_per_call * args.steps * 2),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches_per_call * args.steps * 3),
         "launches_per_call": int(launches_per_call),
         "roofline": roofline, "clocks": clocks,
     }
+    if config4 is not None:
+        line["config4"] = config4
+    if world == 1 and not args.no_sides:
+        try:
+            line["config1"] = latency_config1(conv)
+        except Exception as e:
+            line["config1"] = {"error": f"{type(e).__name__}: {e}"[:240]}
+    if world == 1 and not args.no_cudnn:
+        try:
+            line["cudnn_baseline"] = cudnn_reference(B, secs)
+        except Exception as e:
+            line["cudnn_baseline"] = {"error": f"{type(e).__name__}: {e}"[:240]}
     if world == 1 and not args.no_cpu_baseline:
         v, dt, threads, done = cpu_reference_throughput(args.cpu_clips, secs)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",

@@ -151,6 +151,8 @@ class NativeConverter:
         self.handle = h
         self.device_index = int(device_index)
         self.finalized = False
+        if os.environ.get("OVC_WIDE_VARIANT"):      # tuning experiments: tiling of the 128-column tensor-core kernel
+            self.set_option("wide_variant", int(os.environ["OVC_WIDE_VARIANT"]))
 
     def close(self):
         if getattr(self, "handle", None):
@@ -271,6 +273,8 @@ class NativeConverter:
         import torch
         assert spec.is_cuda and spec.dtype == torch.float32 and spec.is_contiguous() and spec.dim() == 3
         N, S, T = spec.shape
+        if S != self.hp.spec_channels:
+            raise ValueError(f"reference_encoder: spec has {S} channels, the model has spec_channels {self.hp.spec_channels}")
         out = torch.empty(N, self.hp.gin_channels, device=spec.device, dtype=torch.float32)
         st = stream if stream is not None else torch.cuda.current_stream(spec.device)
         rc = self.lib.ovc_reference_encoder(self.handle, C.c_void_p(spec.data_ptr()), N, T, C.c_void_p(out.data_ptr()),

@@ -18,7 +18,6 @@ import torch
 
 from . import utils
 from ._native import NativeConverter
-from .mel_processing import spectrogram_torch
 from .ref_enc import ReferenceEncoder
 from .schema import hot_path_keys, ref_enc_keys, tts_keys
 
@@ -49,7 +48,7 @@ def _load_audio(src: AudioLike, sr: int) -> np.ndarray:
     data = data.astype(np.float32)
     if data.ndim == 2:
         data = data.mean(axis=1)
-    if file_sr != sr:
+    if sr is not None and file_sr != sr:   # sr=None keeps the file's rate (librosa.load(sr=None))
         from math import gcd
         g = gcd(int(file_sr), int(sr))
         data = resample_poly(data, sr // g, file_sr // g).astype(np.float32)
@@ -266,6 +265,8 @@ class BaseSpeakerTTS(OpenVoiceBaseClass):
         sentence gets what its own batch-1 call would give (ragged decode)."""
         speaker_id = self.hps.speakers[speaker] if isinstance(speaker, str) else int(speaker)
         n = len(sequences)
+        if n == 0:      # the reference's loop over zero sentences yields no audio (api.py:79-91)
+            return []
         T = max(len(q) for q in sequences)
         x = torch.zeros(n, T, dtype=torch.int64)
         for i, q in enumerate(sequences):
@@ -301,11 +302,14 @@ class ToneColorConverter(OpenVoiceBaseClass):
         super().__init__(*args, **kwargs)
         self.watermark_model = None
         if enable_watermark:
+            # the reference fails hard at `import wavmark` (openvoice/api.py:105-107); silently returning
+            # un-watermarked audio to a caller who asked for the watermark is worse than failing
             try:
                 import wavmark  # type: ignore
-                self.watermark_model = wavmark.load_model().to(self.device)
-            except ImportError:
-                print("wavmark is not installed: watermarking disabled")
+            except ImportError as e:
+                raise ImportError("ToneColorConverter(enable_watermark=True) needs the third-party `wavmark` package "
+                                  "(openvoice/api.py:105-107); pass enable_watermark=False to convert without it") from e
+            self.watermark_model = wavmark.load_model().to(self.device)
         self.version = getattr(self.hps, "_version_", "v1")
 
     # ------------------------------------------------------------------ speaker embedding
@@ -480,7 +484,9 @@ class ToneColorConverter(OpenVoiceBaseClass):
         assert se.shape[0] == n, "one speaker embedding per utterance (or a single one for all)"
         return se
 
-    def _convert_chunk(self, waves, src, tgt, tau, noise):
+    def _enqueue_chunk(self, waves, src, tgt, tau, noise, slot=0):
+        """Stage, upload and launch one ragged batch on the current stream WITHOUT synchronising the host.
+        Returns (o [B, 256 * Tmax] on the device, frames per item)."""
         hps = self.hps
         hop = hps.data.hop_length
         B = len(waves)
@@ -491,15 +497,26 @@ class ToneColorConverter(OpenVoiceBaseClass):
         dev = self.device
         if min(len(w) for w in waves) <= (hps.data.filter_length - hop) // 2:
             raise ValueError("audio shorter than the STFT reflect padding")   # torch raises here too
-        # host -> device: one pinned staging buffer (cached across calls: cudaHostAlloc is slow), one copy
+        # host -> device: one pinned staging buffer per slot (cached across calls: cudaHostAlloc is slow), one copy;
+        # a slot is restaged only after its previous upload has left it
         Lmax = max(len(w) for w in waves)
-        stage = self._pinned("in", B * Lmax).view(B, Lmax)
+        ev = self.__dict__.setdefault("_h2d_done", {}).get(slot)
+        if ev is not None:
+            ev.synchronize()
+        stage = self._pinned(f"in{slot}", B * Lmax).view(B, Lmax)
+        lens = np.empty(B, dtype=np.int64)
         for b, w in enumerate(waves):
             stage[b, : len(w)] = torch.from_numpy(w)
             if len(w) < Lmax:
                 stage[b, len(w):] = 0.0
+            lens[b] = len(w)
         wav = stage.to(dev, non_blocking=True)
-        wlen = torch.tensor([len(w) for w in waves], dtype=torch.int64, device=dev)
+        lens_pin = self._pinned_i64(f"len{slot}", B)
+        lens_pin.copy_(torch.from_numpy(lens))
+        wlen = lens_pin.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._h2d_done[slot] = ev
         nz = None
         if noise is not None:
             nz = torch.zeros(B, hps.model.inter_channels, Tmax, device=dev, dtype=torch.float32)
@@ -509,11 +526,37 @@ class ToneColorConverter(OpenVoiceBaseClass):
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         # spectrogram + voice_conversion, every item at its own exact length (api.py:148-154)
         o, _ = self.model.native.convert_waveform(wav, wlen, src, tgt, noise=nz, tau=float(tau), seed=seed)
+        return o.view(B, -1), frames
+
+    def _convert_chunk(self, waves, src, tgt, tau, noise):
+        hop = self.hps.data.hop_length
+        o, frames = self._enqueue_chunk(waves, src, tgt, tau, noise)
         host = self._pinned("out", o.numel()).view(o.shape)
         host.copy_(o, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
         audio = host.numpy()
-        return [audio[b, : frames[b] * hop].copy() for b in range(B)]
+        return [audio[b, : frames[b] * hop].copy() for b in range(len(waves))]
+
+    @torch.no_grad()
+    def convert_batch_device(self, audios: Sequence[AudioLike], src_se, tgt_se, tau: float = 0.3, slot: int = 0):
+        """``convert_batch`` up to the device: stages and launches ONE ragged batch asynchronously on the current
+        stream and returns (o [n, max samples] float32 on the device, samples per item).  No host synchronisation,
+        no device -> host copy: the building block of ``distributed.convert_sharded_async`` (waveforms gathered
+        GPU-to-GPU over NCCL) and of pipelined serving.  ``slot`` picks the pinned upload buffer (alternate 0 / 1
+        between in-flight calls)."""
+        waves = [_load_audio(a, self.hps.data.sampling_rate) for a in audios]
+        n = len(waves)
+        o, frames = self._enqueue_chunk(waves, self._stack_se(src_se, n), self._stack_se(tgt_se, n), tau, None, slot)
+        hop = self.hps.data.hop_length
+        return o, [f * hop for f in frames]
+
+    def _pinned_i64(self, name, numel):
+        cache = self.__dict__.setdefault("_pin_cache", {})
+        buf = cache.get(name)
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(int(numel) + 64, dtype=torch.int64).pin_memory()
+            cache[name] = buf
+        return buf[:numel]
 
     def _pinned(self, name, numel):
         """Grow-only pinned host staging buffers."""
@@ -552,6 +595,8 @@ class ToneColorConverter(OpenVoiceBaseClass):
 
     def detect_watermark(self, audio, n_repeat):
         """Decode ``n_repeat`` chunks back to text (openvoice/api.py:186-201); "Fail" when the audio is too short."""
+        if self.watermark_model is None:
+            raise RuntimeError("detect_watermark needs the wavmark model: construct with enable_watermark=True")
         rows = []
         for n, sl, full in self._wm_chunks(audio, n_repeat):
             if not full:

@@ -34,6 +34,24 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// every ABI entry point runs on its context's device and puts the caller's current device back on exit (PyTorch
+// reads the current device through cudaGetDevice: a converter on cuda:N must not move the caller's default)
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE(c)                                                                              \
+  DeviceGuard dev_guard_((c)->device);                                                            \
+  if (!dev_guard_.ok) return fail(OVC_ERR_CUDA, "cudaSetDevice(%d) failed", (c)->device)
+
 #define CK(expr)                                                                                  \
   do {                                                                                            \
     cudaError_t e_ = (expr);                                                                      \
@@ -174,6 +192,7 @@ struct ovc_ctx {
   bool has_refenc = false;
   size_t re_conv_w[6] = {0}, re_conv_b[6] = {0}, re_wih = 0, re_whh = 0, re_bih = 0, re_bhh = 0, re_pw = 0, re_pb = 0,
          re_lng = 0, re_lnb = 0;
+  int re_gru_in = 0;           // columns of ref_enc.gru.weight_ih_l0
   float* d_re = nullptr;
   size_t re_floats = 0;
 
@@ -344,7 +363,7 @@ static int pack_wn(ovc_ctx* c, const std::string& prefix, int n_layers, WNLayers
   return 0;
 }
 
-// tensor-core copy of a conv: fp16 [n_tile][Cin/16][K][hi|lo][column block][TN][8]: hi = fp16(w), lo = fp16((w - hi) * 2^11)
+// tensor-core copy of a conv: fp16 [n_tile][Cin/16][K][column block][hi|lo][TN][8]: hi = fp16(w), lo = fp16((w - hi) * 2^11)
 // (ovc_tc.cuh), laid out exactly as the kernel's shared-memory operand slots (one TMA bulk copy per slot)
 template <class WF, class BF>
 static TcLayer pack_tc(ovc_ctx* c, int Ntot, int Cin, int K, int DIL, WF wfun, BF bfun) {
@@ -367,8 +386,8 @@ static TcLayer pack_tc(ovc_ctx* c, int Ntot, int Cin, int K, int DIL, WF wfun, B
               const float w = wfun(nt * T.TN + n, k16 * 16 + kc * 8 + e, tap);
               const __half hi = __float2half_rn(w);
               const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
-              sl[((0 * 2 + kc) * T.TN + n) * 8 + e] = __half_as_ushort(hi);
-              sl[((1 * 2 + kc) * T.TN + n) * 8 + e] = __half_as_ushort(lo);
+              sl[((kc * 2 + 0) * T.TN + n) * 8 + e] = __half_as_ushort(hi);   // rows [0, TN) of the 2*TN-row operand
+              sl[((kc * 2 + 1) * T.TN + n) * 8 + e] = __half_as_ushort(lo);   // rows [TN, 2*TN)
             }
       }
   T.b_off = round_up(c->h_tcw.size(), 64);
@@ -609,6 +628,15 @@ static int finalize(ovc_ctx* c) {
     if (wih->shape[0] != 384 || whh->shape[0] != 384 || whh->shape[1] != 128 || rpw->shape[0] != G || rpw->shape[1] != 128 ||
         lng->shape[0] != S)
       return fail(OVC_ERR_INVALID, "ref_enc.* tensors have the wrong shape");
+    {
+      int w6 = S;   // width after the six stride-2 convs (models.py:330-337)
+      for (int i = 0; i < 6; ++i) w6 = (w6 - 1) / 2 + 1;
+      if (wih->shape.size() != 2 || wih->shape[1] != 128 * w6 || bih->numel() != 384 || bhh->numel() != 384 ||
+          lnb->numel() != S || rpb->numel() != G)
+        return fail(OVC_ERR_INVALID, "ref_enc.gru / layernorm / proj tensors do not match spec_channels %d (GRU input %d expected)",
+                    S, 128 * w6);
+      c->re_gru_in = 128 * w6;
+    }
     c->re_wih = put(wih->data); c->re_whh = put(whh->data); c->re_bih = put(bih->data); c->re_bhh = put(bhh->data);
     c->re_pw = put(rpw->data); c->re_pb = put(rpb->data); c->re_lng = put(lng->data); c->re_lnb = put(lnb->data);
     c->has_refenc = true;
@@ -622,7 +650,7 @@ static int finalize(ovc_ctx* c) {
 #undef NEED
 #undef WEFF
   // ---- upload
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
   if (c->d_w) { cudaFree(c->d_w); c->d_w = nullptr; }
   c->w_floats = c->h_w.size();
   CK(cudaMalloc(&c->d_w, c->w_floats * sizeof(float)));
@@ -1227,7 +1255,7 @@ int ovc_create(const ovc_hparams* hp, int device, ovc_ctx** out) {
 
 void ovc_destroy(ovc_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard_(c->device);
   if (c->d_w) cudaFree(c->d_w);
   if (c->d_ws) cudaFree(c->d_ws);
   if (c->d_tts) cudaFree(c->d_tts);
@@ -1276,7 +1304,7 @@ int ovc_voice_conversion(ovc_ctx* c, const float* spec, const int64_t* lengths, 
   if (B < 1 || Tmax < 1) return fail(OVC_ERR_INVALID, "B and Tmax must be positive (got %d, %d)", B, Tmax);
   if ((long long)Tmax * 256 * 64 > 2000000000LL) return fail(OVC_ERR_INVALID, "Tmax %d too large for 32-bit indexing", Tmax);
   if (B > 65535) return fail(OVC_ERR_INVALID, "B %d exceeds the grid limit", B);
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
   c->ev_used = c->prof ? c->ev_used : 0;
   return run_vc(c, spec, Tmax, (const long long*)lengths, g_src, g_tgt, noise, seed, tau, B, Tmax, ragged, o_hat, z, z_p, z_hat,
                 (cudaStream_t)stream);
@@ -1300,7 +1328,7 @@ int ovc_spectrogram(ovc_ctx* c, const float* wav, const int64_t* wav_lengths, in
   if (!c->finalized) return fail(OVC_ERR_STATE, "ovc_finalize_weights has not been called");
   if (!wav || !wav_lengths || !spec) return fail(OVC_ERR_INVALID, "null tensor argument");
   if (B < 1 || Lmax < 1 || Tmax < 1 || B > 65535) return fail(OVC_ERR_INVALID, "bad sizes B=%d Lmax=%d Tmax=%d", B, Lmax, Tmax);
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
   return launch_stft(c, wav, wav_lengths, B, Lmax, Tmax, spec, Tmax, (long long*)frames, (cudaStream_t)stream);
 }
 
@@ -1313,7 +1341,7 @@ int ovc_convert_waveform(ovc_ctx* c, const float* wav, const int64_t* wav_length
   const int Tmax = Lmax / c->hp.hop_length;
   if (B < 1 || Tmax < 1 || B > 65535) return fail(OVC_ERR_INVALID, "bad sizes B=%d Lmax=%d", B, Lmax);
   if ((long long)Tmax * 256 * 64 > 2000000000LL) return fail(OVC_ERR_INVALID, "Lmax %d too large for 32-bit indexing", Lmax);
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
   cudaStream_t st = (cudaStream_t)stream;
   const WsLayout W = ws_layout(c, B, Tmax);
   TRY(ensure_ws(c, W, B, Tmax, st));
@@ -1331,7 +1359,7 @@ int ovc_reference_encoder(ovc_ctx* c, const float* spec, int N, int T, float* ou
   if (!c->finalized) return fail(OVC_ERR_STATE, "ovc_finalize_weights has not been called");
   if (!c->has_refenc) return fail(OVC_ERR_MISSING, "the checkpoint had no ref_enc.* tensors");
   if (!spec || !out || N < 1 || T < 1) return fail(OVC_ERR_INVALID, "bad argument to ovc_reference_encoder");
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
   cudaStream_t st = (cudaStream_t)stream;
   const int F = c->hp.spec_channels, G = c->hp.gin_channels;
   static const int filt[7] = {1, 32, 32, 64, 64, 128, 128};
@@ -1342,7 +1370,8 @@ int ovc_reference_encoder(ovc_ctx* c, const float* spec, int N, int T, float* ou
     H[i + 1] = (H[i] - 1) / 2 + 1; W[i + 1] = (W[i] - 1) / 2 + 1;
     maxact = std::max(maxact, (size_t)N * filt[i + 1] * H[i + 1] * W[i + 1]);
   }
-  if ((size_t)filt[6] * W[6] != 1152 && false) return fail(OVC_ERR_INVALID, "unexpected GRU input width");
+  if (128 * W[6] != c->re_gru_in)
+    return fail(OVC_ERR_INVALID, "ref_enc.gru.weight_ih_l0 takes %d inputs but spec_channels %d gives %d", c->re_gru_in, F, 128 * W[6]);
   const size_t gi_floats = (size_t)N * H[6] * 384;
   const size_t need = 2 * round_up(maxact, 64) + round_up(gi_floats, 64);
   if (need > c->re_floats) {
@@ -1398,7 +1427,7 @@ int ovc_tts_encode(ovc_ctx* c, const int64_t* tokens, const int64_t* x_lengths, 
   if (B < 1 || T < 1) return fail(OVC_ERR_INVALID, "B and T must be positive (got %d, %d)", B, T);
   if (B > 65535 || (long long)T * T > 2000000000LL / 256) return fail(OVC_ERR_INVALID, "B %d / T %d exceed the grid limits", B, T);
   if (!(length_scale > 0.f)) return fail(OVC_ERR_INVALID, "length_scale must be positive");
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
   c->ev_used = c->prof ? c->ev_used : 0;
   return run_tts_encode(c, (const long long*)tokens, (const long long*)x_lengths, (const long long*)sid, noise_w, seed,
                         noise_scale_w, length_scale, sdp_ratio, B, T, (long long*)y_lengths, w_ceil, logw, (cudaStream_t)stream);
@@ -1413,7 +1442,7 @@ int ovc_tts_decode(ovc_ctx* c, const float* noise, uint64_t seed, float noise_sc
   if (!o) return fail(OVC_ERR_INVALID, "null tensor argument");
   if (Ymax < 1) return fail(OVC_ERR_INVALID, "Ymax must be positive");
   if ((long long)Ymax * 256 * 64 > 2000000000LL) return fail(OVC_ERR_INVALID, "Ymax %d too large for 32-bit indexing", Ymax);
-  CK(cudaSetDevice(c->device));
+  ON_DEVICE(c);
   c->ev_used = c->prof ? c->ev_used : 0;
   if (max_len < 0) return fail(OVC_ERR_INVALID, "max_len must be >= 0 (0 = no limit)");
   return run_tts_decode(c, noise, seed, noise_scale, B, Ymax, max_len, ragged, o, z, z_p, (cudaStream_t)stream);
@@ -1513,7 +1542,7 @@ int ovc_debug_fetch(ovc_ctx* c, const char* name, float* host_out, size_t max_fl
   if (shape4) memcpy(shape4, d.shape, sizeof d.shape);
   if (host_out) {
     if (max_floats < n) return fail(OVC_ERR_INVALID, "buffer too small for tap '%s': need %zu floats", name, n);
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host_out, d.d, n * sizeof(float), cudaMemcpyDeviceToHost));
   }

@@ -6,7 +6,10 @@
 // hi = fp16(x), lo = fp16((x - hi) * 2^11) (22 mantissa bits, ovc_tc.cuh) and every product is evaluated as
 // a_hi*b_hi + (a_lo*b_hi + a_hi*b_lo) / 2^11 by tcgen05.mma.kind::f16 with fp32 accumulation in TMEM: the hi*hi
 // products in one accumulator, the two cross terms in a second one ("low-order accumulator"), joined in the
-// epilogue.  Besides carrying the 2^-11 scale, the second accumulator keeps the tensor core's truncating adds
+// epilogue.  The two accumulators of a tile sit side by side in TMEM and a weight slot holds [b_hi ; b_lo] as ONE
+// 2*TN-row operand, so a_hi * [b_hi ; b_lo]^T is a single MMA of width 2*TN (both accumulators at once) and
+// a_lo * b_hi^T a second one of width TN: two A-operand reads per k-step instead of three (SS-mode MMAs of the
+// narrow layers are bound by shared-memory operand reads, 128 B/clk).  Besides carrying the 2^-11 scale, the second accumulator keeps the tensor core's truncating adds
 // (tools/tc_acc_test.cu) away from the long hi*hi sum.  Error ~1e-6 per conv, i.e. fp32-grade
 // (tools/tc_f16_test.cu); fp16 MMAs run at twice the TF32 rate on half the operand bytes.
 //
@@ -22,7 +25,7 @@ namespace ovc {
 
 struct TcConvArgs {
   const float* x; long long x_bs;     // [B][Lpitch][Cin]
-  const uint16_t* w;                   // packed fp16 [n_tile][Cin/16][K][hi|lo][2 (8-channel column block)][TN][8]
+  const uint16_t* w;                   // packed fp16 [n_tile][Cin/16][K][2 (8-channel column block)][hi|lo][TN][8]
   const float* bias; long long bias_bs; // [Ntot] (+ b * bias_bs: per-utterance speaker-conditioning bias of the WN gate)
   float* y; long long y_bs; int y_ld;  // [B][Lpitch][y_ld]
   const float* r;                      // residual, same geometry as y (nullable)
@@ -73,8 +76,8 @@ __device__ __forceinline__ void tc_item(int i, int& row, int& kc) {
 }
 
 // Epilogue of MMA tiles [mt_lo, mt_hi) of one CTA tile (MT x 128 steps x TN columns): TMEM -> registers -> fused ops
-// -> global.  Warp w may read TMEM lanes [32*(w%4), +32); acc = main accumulators (MT*TN columns), the low-order
-// ones MT*TN columns after.
+// -> global.  Warp w may read TMEM lanes [32*(w%4), +32); tile mt owns columns [2*mt*TN, +TN) (main accumulator) and
+// the next TN (low-order accumulator).
 template <int TN, int MT>
 __device__ __forceinline__ void tc_epilogue(const TcConvArgs& a, uint32_t acc, int b, int t0, int n0, int lim, int warp, int lane,
                                             int mt_lo, int mt_hi) {
@@ -106,12 +109,12 @@ __device__ __forceinline__ void tc_epilogue(const TcConvArgs& a, uint32_t acc, i
       }
       uint32_t rm[32];
       float v[32];
-      tc::tmem_ld32_issue(acc + ((uint32_t)lane_base << 16) + mt * TN + c0, rm);
+      tc::tmem_ld32_issue(acc + ((uint32_t)lane_base << 16) + 2 * mt * TN + c0, rm);
       tc::tmem_ld_wait(rm);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rm[i]);
       if (two) {
-        tc::tmem_ld32_issue(acc + ((uint32_t)lane_base << 16) + (MT + mt) * TN + c0, rm);
+        tc::tmem_ld32_issue(acc + ((uint32_t)lane_base << 16) + (2 * mt + 1) * TN + c0, rm);
         tc::tmem_ld_wait(rm);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(rm[i]), tc::kLoInv, v[i]);
@@ -175,16 +178,16 @@ __device__ __forceinline__ void tc_epilogue(const TcConvArgs& a, uint32_t acc, i
   }
 }
 
-// one thread issues the MMAs of MMA tiles [mt_lo, mt_hi) for one staged A chunk (KS k-steps of 16 channels, all taps)
-// against the weight slots the ring delivers in [k-step][tap] order
+// one thread issues the MMAs of MMA tiles [mt_lo, mt_hi) for one (k-step, tap) against weight slot b_slot = [b_hi ; b_lo]
 #define OVC_TC_ISSUE_MMAS(ACC)                                                                       \
   _Pragma("unroll") for (int mt = mt_lo; mt < mt_hi; ++mt) {                                         \
     const uint64_t ad_hi = a_cur + mt * 128, ad_lo = ad_hi + A_LO16;                                 \
-    const uint32_t d = (ACC) + mt * TN, dl = (ACC) + (MT + mt) * TN;                                 \
-    tc::mma_f16(d, ad_hi, bd_hi, idesc, !first);                                                     \
+    const uint32_t d = (ACC) + 2 * mt * TN;                                                          \
     if (three) {                                                                                     \
-      tc::mma_f16(dl, ad_lo, bd_hi, idesc, !first);                                                  \
-      tc::mma_f16(dl, ad_hi, bd_lo, idesc, true);                                                    \
+      tc::mma_f16(d, ad_hi, b_slot, idesc2, !first);      /* [main | low] (+)= a_hi * [b_hi ; b_lo]^T */ \
+      tc::mma_f16(d + TN, ad_lo, b_slot, idesc1, true);   /* low += a_lo * b_hi^T */                 \
+    } else {                                                                                         \
+      tc::mma_f16(d, ad_hi, b_slot, idesc1, !first);                                                 \
     }                                                                                                \
   }
 
@@ -208,7 +211,7 @@ struct TcwCfg {
   static constexpr int RAWD = 2, NST = RAWD + 1;                  // raw fp32 landing stages in flight ahead
   static constexpr int SLOTS = MT == 1 ? 6 : 14;                  // weight ring depth
   static constexpr int A_BUF_BYTES = 2 * NKC * ROWS * 16;         // [hi|lo][column block][row][8 halfs]
-  static constexpr int SLOT_BYTES = 2 * 2 * TN * 16;              // [hi|lo][column block][n][8 halfs]
+  static constexpr int SLOT_BYTES = 2 * 2 * TN * 16;              // [column block][hi|lo][n][8 halfs]
   static constexpr int RAW_BYTES = ROWS * KCH * 4;
   static constexpr size_t SMEM_BYTES = 512 + NABUF * A_BUF_BYTES + SLOTS * SLOT_BYTES + NST * RAW_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * MT * TN;              // main + low-order accumulators
@@ -260,9 +263,7 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
     // ------------------------------------------------------------ weight producer (TMA bulk)
     if (lane == 0) {
       const unsigned char* wp = reinterpret_cast<const unsigned char*>(a.w) + (size_t)blockIdx.y * n_slots * Cfg::SLOT_BYTES;
-      // a slot is [hi | lo]; single-pass fp16 needs (and fetches) only the first half
-      const uint32_t BYTES = a.passes == 3 ? Cfg::SLOT_BYTES : Cfg::SLOT_BYTES / 2;
-      const uint32_t PART = BYTES / CL;
+      constexpr uint32_t BYTES = Cfg::SLOT_BYTES, PART = BYTES / CL;
       int slot = 0;
       uint32_t phase = 1;   // the first pass over the ring finds every slot free
       for (int it = 0; it < n_slots; ++it) {
@@ -282,10 +283,9 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
     // are advanced by plain adds.
     if (lane == 0) {
       const int mt_lo = (warp == 1 ? 0 : MT / NISS), mt_hi = mt_lo + MT / NISS;
-      const uint32_t idesc = tc::make_idesc_f16(128, TN);
-      constexpr uint32_t LBO_A = ROWS * 16, LBO_B = TN * 16, SBO = 128;
+      const uint32_t idesc1 = tc::make_idesc_f16(128, TN), idesc2 = tc::make_idesc_f16(128, 2 * TN);
+      constexpr uint32_t LBO_A = ROWS * 16, LBO_B = 2 * TN * 16, SBO = 128;
       constexpr uint32_t A_LO16 = (NKC * ROWS * 16) >> 4;        // hi -> lo inside an A buffer, in 16-byte units
-      constexpr uint32_t B_LO16 = (2 * TN * 16) >> 4;
       constexpr uint32_t SLOT16 = Cfg::SLOT_BYTES >> 4;
       const uint64_t a_proto = tc::make_desc(0, LBO_A, SBO), b_proto = tc::make_desc(0, LBO_B, SBO);
       const uint64_t b_ring = b_proto + (tc::smem_addr(bring) >> 4);
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
           for (int tap = 0; tap < a.K; ++tap) {
             mbar_wait(&b_full[slot], bphase);
             tc::fence_after();
-            const uint64_t bd_hi = b_ring + (uint32_t)slot * SLOT16, bd_lo = bd_hi + B_LO16;
+            const uint64_t b_slot = b_ring + (uint32_t)slot * SLOT16;
             if (active) {
               // output step (t0 + mt*128 + i) reads staged row (mt*128 + i + tap*DIL): the halo tile starts at t0 - H
               OVC_TC_ISSUE_MMAS(tmem_d)
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcC
   const int nq = a.Cin / Cfg::KCH;
   const int n_slots = (a.Cin / 16) * a.K;
   const bool resident = n_slots <= RING;
-  const uint32_t BYTES = a.passes == 3 ? Cfg::SLOT_BYTES : Cfg::SLOT_BYTES / 2;
+  constexpr uint32_t BYTES = Cfg::SLOT_BYTES;
 
   if (tid == 0) {
     for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 2); }
@@ -472,9 +472,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcC
     // ------------------------------------------------------------ MMA issuers (each owns half of the MMA tiles)
     if (lane == 0) {
       const int mt_lo = (warp - 1) * (MT / 2), mt_hi = mt_lo + MT / 2;
-      const uint32_t idesc = tc::make_idesc_f16(128, TN);
-      constexpr uint32_t LBO_A = ROWS * 16, LBO_B = TN * 16, SBO = 128;
-      constexpr uint32_t A_LO16 = (NKC * ROWS * 16) >> 4, B_LO16 = (2 * TN * 16) >> 4, SLOT16 = Cfg::SLOT_BYTES >> 4;
+      const uint32_t idesc1 = tc::make_idesc_f16(128, TN), idesc2 = tc::make_idesc_f16(128, 2 * TN);
+      constexpr uint32_t LBO_A = ROWS * 16, LBO_B = 2 * TN * 16, SBO = 128;
+      constexpr uint32_t A_LO16 = (NKC * ROWS * 16) >> 4, SLOT16 = Cfg::SLOT_BYTES >> 4;
       const uint64_t a_proto = tc::make_desc(0, LBO_A, SBO), b_proto = tc::make_desc(0, LBO_B, SBO);
       const uint64_t b_ring = b_proto + (tc::smem_addr(bring) >> 4);
       const uint32_t dil = (uint32_t)a.DIL;
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcC
                 mbar_wait(&b_full[slot], resident ? 0u : bphase);
                 tc::fence_after();
               }
-              const uint64_t bd_hi = b_ring + (uint32_t)slot * SLOT16, bd_lo = bd_hi + B_LO16;
+              const uint64_t b_slot = b_ring + (uint32_t)slot * SLOT16;
               OVC_TC_ISSUE_MMAS(acc)
               first = false;
               if (!resident) tc::mma_commit(&b_empty[slot]);

@@ -4,6 +4,11 @@ Utterances are independent, so N GPUs = N replicas of the model, one process per
 (``torchrun``), no collective inside the hot path.  ``torch.distributed`` (NCCL over NVLink on
 GPUs, gloo in the CPU tests) is used for exactly two things, as north_star prescribes:
 broadcasting the checkpoint from rank 0 and gathering the output waveforms on rank 0.
+
+Two gather paths: ``convert_sharded`` takes any ``convert_fn`` returning host arrays (host staging; what the CPU / gloo
+tests drive), ``convert_sharded_async`` keeps the converted batch on the device, gathers it GPU-to-GPU (NCCL over
+NVLink) on a side stream and copies it to pinned host memory on rank 0 only, so step i's gather and download overlap
+step i+1's kernels.
 """
 from __future__ import annotations
 
@@ -108,3 +113,119 @@ def convert_sharded(convert_fn: Callable[..., List[np.ndarray]], audios: Sequenc
     res = convert_fn([audios[i] for i in mine], pick(src_se),
                      [tgt_se[i] for i in mine] if isinstance(tgt_se, (list, tuple)) else tgt_se, **kw) if mine else []
     return gather_waveforms(res, mine, len(audios), device=device)
+
+
+class ShardedJob:
+    """Handle of one ``convert_sharded_async`` call.  ``result()`` blocks until rank ``dst`` holds every waveform in
+    pinned host memory and returns them in the original order (views into a buffer that the second-next call on
+    the same converter reuses; ``copy=True`` detaches them); the other ranks get ``None``."""
+
+    def __init__(self, done, table, host, rank, dst, n_total, copy):
+        self._done, self._table, self._host = done, table, host
+        self._rank, self._dst, self._n, self._copy = rank, dst, n_total, copy
+
+    def result(self) -> Optional[List[np.ndarray]]:
+        if self._done is not None:
+            self._done.synchronize()
+        if self._rank != self._dst:
+            return None
+        out: List[Optional[np.ndarray]] = [None] * self._n
+        for r, rows in enumerate(self._table):
+            block = self._host[r]
+            for j, (i, n) in enumerate(rows):
+                a = block[j, :n]
+                out[i] = a.copy() if self._copy else a
+        assert all(o is not None for o in out)
+        return out  # type: ignore[return-value]
+
+
+def convert_sharded_async(converter, audios: Sequence[np.ndarray], src_se, tgt_se, tau: float = 0.3, dst: int = 0,
+                          copy: bool = False) -> ShardedJob:
+    """Every rank holds the same utterance list; each enqueues its LPT shard with
+    ``converter.convert_batch_device`` (no host sync), the padded result blocks are gathered on rank ``dst`` by
+    ONE device-to-device collective on a side stream, and rank ``dst`` alone downloads them.  Shapes of every
+    rank's block follow from the shared list, so no size exchange is needed.  Returns at once; call ``.result()``.
+    ``src_se`` / ``tgt_se``: one embedding for all items, or a per-item sequence."""
+    import torch
+    rank, world = _world()
+    hop = converter.hps.data.hop_length
+    samples = [len(a) // hop * hop for a in audios]
+    shards = lpt_shard([len(a) for a in audios], world)
+    n_max = max(len(sh) for sh in shards)
+    l_max = max(samples) if samples else 0
+    mine = shards[rank]
+    pick = (lambda se: [se[i] for i in mine]) if isinstance(src_se, (list, tuple)) else (lambda se: se)
+    state = converter.__dict__.setdefault("_shard_state", {"n": 0})
+    k = state["n"] % 2
+    state["n"] += 1
+    if mine:
+        o, _ = converter.convert_batch_device([audios[i] for i in mine], pick(src_se),
+                                              [tgt_se[i] for i in mine] if isinstance(tgt_se, (list, tuple)) else tgt_se,
+                                              tau=tau, slot=k)
+    else:
+        o = torch.zeros(0, max(l_max, 1), dtype=torch.float32, device=converter.device)
+    table = [[(i, samples[i]) for i in sh] for sh in shards]
+    dev = o.device
+    if world == 1:
+        host = _pinned_block(state, f"h{k}", (1, max(n_max, 1), max(l_max, 1)), dev)
+        done = None
+        if len(mine):
+            host[0, : o.shape[0], : o.shape[1]].copy_(o, non_blocking=True)
+        if dev.type == "cuda":
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+        return ShardedJob(done, table, host.numpy(), rank, dst, len(audios), copy)
+    # fixed-shape block per rank (pad rows / columns), gathered on a side stream
+    cuda = dev.type == "cuda"
+    if cuda:
+        side = state.get("side")
+        if side is None:
+            side = state["side"] = torch.cuda.Stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+    block = o
+    if o.shape[0] != n_max or o.shape[1] != l_max:
+        block = torch.zeros(n_max, max(l_max, 1), dtype=torch.float32, device=dev)
+        block[: o.shape[0], : o.shape[1]] = o
+        if cuda:
+            ready.record(torch.cuda.current_stream(dev))
+    host = None
+    done = None
+    ctx = torch.cuda.stream(side) if cuda else _nullcontext()
+    with ctx:
+        if cuda:
+            side.wait_event(ready)
+            block.record_stream(side)
+        blocks = [torch.empty_like(block) for _ in range(world)] if rank == dst else None
+        dist.gather(block, blocks, dst=dst)
+        if rank == dst:
+            host = _pinned_block(state, f"h{k}", (world, n_max, max(l_max, 1)), dev)
+            for r in range(world):
+                host[r].copy_(blocks[r], non_blocking=True)
+                if cuda:
+                    blocks[r].record_stream(side)
+        if cuda:
+            done = torch.cuda.Event()
+            done.record(side)
+    return ShardedJob(done, table, host.numpy() if host is not None else None, rank, dst, len(audios), copy)
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+def _pinned_block(state, name, shape, dev):
+    """Grow-only host buffers (pinned when the data comes from a GPU), two generations alternate."""
+    import torch
+    numel = int(np.prod(shape))
+    buf = state.get(name)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(int(numel * 1.1) + 1024, dtype=torch.float32)
+        if dev.type == "cuda":
+            buf = buf.pin_memory()
+        state[name] = buf
+    return buf[:numel].view(shape)

@@ -41,6 +41,9 @@ def get_se(audio_path, vc_model, target_dir="processed", vad=True, splitter=None
     base = os.path.basename(audio_path).rsplit(".", 1)[0] if isinstance(audio_path, str) else "array"
     audio_name = f"{base}_{version}_{hash_numpy_array(audio)}"
     se_path = os.path.join(target_dir, audio_name, "se.pth")
+    if os.path.isfile(se_path):   # openvoice/se_extractor.py:139-142: reuse the cached embedding
+        import torch
+        return torch.load(se_path).to(vc_model.device), audio_name
     segs = (splitter or split_audio_fixed)(audio, sr)
     if len(segs) == 0:
         raise NotImplementedError("No audio segments found!")

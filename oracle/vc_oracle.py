@@ -238,7 +238,7 @@ def _w(sd: StateDict, prefix: str) -> torch.Tensor:
 
 def sequence_mask(lengths: torch.Tensor, T: int, dtype) -> torch.Tensor:
     """[B,1,T] float mask, t < length (openvoice/commons.py:121-125, models.py:213)."""
-    return (torch.arange(T)[None, :] < lengths[:, None]).unsqueeze(1).to(dtype)
+    return (torch.arange(T, device=lengths.device)[None, :] < lengths[:, None]).unsqueeze(1).to(dtype)
 
 
 def wn_forward(sd: StateDict, prefix: str, x: torch.Tensor, mask: torch.Tensor,

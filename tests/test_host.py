@@ -187,6 +187,30 @@ if rank == 0:
         assert np.array_equal(o, (-a[: 256 * (len(a) // 256)] * 0.5).astype(np.float32))
 else:
     assert out is None
+# the device-gather path (convert_sharded_async) with a stand-in converter that keeps its batch in a tensor
+from openvoice_b200.distributed import convert_sharded_async
+class FakeConverter:
+    class hps:
+        class data:
+            hop_length = 256
+    device = torch.device("cpu")
+    def convert_batch_device(self, batch, src, tgt, tau=0.3, slot=0):
+        n = [256 * (len(a) // 256) for a in batch]
+        o = torch.zeros(len(batch), max(n))
+        for j, a in enumerate(batch):
+            o[j, : n[j]] = torch.from_numpy(-a[: n[j]] * tau)
+        return o, n
+fc = FakeConverter()
+long = [a for a in audios if len(a) >= 256]
+jobs = [convert_sharded_async(fc, long, None, None, tau=t) for t in (0.5, 0.25, 2.0)]     # three calls in flight
+for t, job in ((0.25, jobs[1]), (2.0, jobs[2])):        # the two youngest are still intact (two buffer generations)
+    res = job.result()
+    if rank == 0:
+        assert len(res) == len(long)
+        for a, o in zip(long, res):
+            assert np.array_equal(o, (-a[: 256 * (len(a) // 256)] * t).astype(np.float32))
+    else:
+        assert res is None
 dist.barrier()
 dist.destroy_process_group()
 sys.stdout.write(f"worker-{rank}-ok\n"); sys.stdout.flush()

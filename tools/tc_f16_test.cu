@@ -1,6 +1,7 @@
 // Validates the fp16 tcgen05 building blocks of ovc_tc.cuh on a B200:
 //   D[128 x N] = A[shift .. shift+128) x B^T   (K-major, no swizzle, kind::f16, fp32 accumulate in TMEM)
-// (1) single-pass fp16, (2) 3xFP16 split precision with the scaled low-order accumulator, (3) row-shifted A
+// (1) single-pass fp16, (2) 3xFP16 split precision with the scaled low-order accumulator: a_hi * [b_hi ; b_lo]^T as ONE
+// MMA of width 2N plus a_lo * b_hi^T, (3) row-shifted A
 // (a convolution tap), (4) small-magnitude operands (fp16 subnormal range of the high parts).
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I openvoice_b200/csrc -o /tmp/tc_f16_test tools/tc_f16_test.cu
 #include <cmath>
@@ -19,9 +20,8 @@ __global__ void __launch_bounds__(128) gemm_test(const float* A, const float* B,
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* a_hi = smem;                                   // [K/8][ROWS_A][8 halfs]
   unsigned char* a_lo = a_hi + ROWS_A * K * 2;
-  unsigned char* b_hi = a_lo + ROWS_A * K * 2;                  // [K/8][N][8 halfs]
-  unsigned char* b_lo = b_hi + N * K * 2;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + N * K * 2);
+  unsigned char* b_st = a_lo + ROWS_A * K * 2;                  // [K/8][hi|lo][N][8 halfs]: one 2N-row operand [b_hi ; b_lo]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(b_st + 2 * N * K * 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(128) gemm_test(const float* A, const float* B,
     const float4 v1 = *reinterpret_cast<const float4*>(B + (size_t)row * K + kc * 8 + 4);
     uint4 hi, lo;
     tc::split_f16x8(v0, v1, 1.f, hi, lo);
-    *reinterpret_cast<uint4*>(b_hi + (kc * N + row) * 16) = hi;
-    *reinterpret_cast<uint4*>(b_lo + (kc * N + row) * 16) = lo;
+    *reinterpret_cast<uint4*>(b_st + ((kc * 2 + 0) * N + row) * 16) = hi;
+    *reinterpret_cast<uint4*>(b_st + ((kc * 2 + 1) * N + row) * 16) = lo;
   }
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -55,17 +55,17 @@ __global__ void __launch_bounds__(128) gemm_test(const float* A, const float* B,
   const uint32_t tmem_d = *tmem_slot;
 
   if (tid == 0) {
-    const uint32_t idesc = tc::make_idesc_f16(M, N);
-    const uint32_t lbo_a = ROWS_A * 16, lbo_b = N * 16, sbo = 128;
+    const uint32_t idesc1 = tc::make_idesc_f16(M, N), idesc2 = tc::make_idesc_f16(M, 2 * N);
+    const uint32_t lbo_a = ROWS_A * 16, lbo_b = 2 * N * 16, sbo = 128;
     for (int k16 = 0; k16 < K / 16; ++k16) {
       const uint64_t ah = tc::make_desc(tc::smem_addr(a_hi) + (2 * k16) * lbo_a + shift * 16, lbo_a, sbo);
       const uint64_t al = tc::make_desc(tc::smem_addr(a_lo) + (2 * k16) * lbo_a + shift * 16, lbo_a, sbo);
-      const uint64_t bh = tc::make_desc(tc::smem_addr(b_hi) + (2 * k16) * lbo_b, lbo_b, sbo);
-      const uint64_t bl = tc::make_desc(tc::smem_addr(b_lo) + (2 * k16) * lbo_b, lbo_b, sbo);
-      tc::mma_f16(tmem_d, ah, bh, idesc, k16 > 0);
+      const uint64_t bs = tc::make_desc(tc::smem_addr(b_st) + (2 * k16) * lbo_b, lbo_b, sbo);
       if (split) {
-        tc::mma_f16(tmem_d + N, al, bh, idesc, k16 > 0);
-        tc::mma_f16(tmem_d + N, ah, bl, idesc, true);
+        tc::mma_f16(tmem_d, ah, bs, idesc2, k16 > 0);       // [main | low] (+)= a_hi * [b_hi ; b_lo]^T
+        tc::mma_f16(tmem_d + N, al, bs, idesc1, true);      // low += a_lo * b_hi^T
+      } else {
+        tc::mma_f16(tmem_d, ah, bs, idesc1, k16 > 0);
       }
     }
     tc::mma_commit(bar);
