@@ -177,9 +177,9 @@ OVC_API int ovc_tts_decode(ovc_ctx* ctx, const float* noise, uint64_t seed, floa
 OVC_API int ovc_set_precision(ovc_ctx* ctx, int mode);
 
 /* Tuning / diagnostics switches (never change results beyond fp32 reordering):
- *   OVC_OPT_WIDE_VARIANT  tiling of the 128-column tensor-core kernel: 0 (default) 128-step tiles, two CTAs per SM,
- *                         2-CTA clusters multicasting the weight stream; 1: 256-step tiles, one CTA per SM; 2: as 0
- *                         without clusters
+ *   OVC_OPT_WIDE_VARIANT  kernel of the 128-column tensor-core layers: 0 (default) the persistent kernel (one CTA per
+ *                         SM, TMA-staged activations, overlapped epilogue); 1: one 256-step tile per CTA; 2: one
+ *                         128-step tile per CTA, two CTAs per SM
  *   OVC_OPT_TTS_SIMPLE    1: one-thread-per-element text-side kernels (the CPU-checked element functions) instead of
  *                         the warp-cooperative LayerNorm / fused attention
  *   OVC_OPT_GRAPH         1 (default): replay the launch sequence of a repeated (shape, buffers) call from a CUDA graph */

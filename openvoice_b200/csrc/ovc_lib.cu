@@ -370,8 +370,8 @@ static TcLayer pack_tc(ovc_ctx* c, int Ntot, int Cin, int K, int DIL, WF wfun, B
   TcLayer T;
   T.Cin = Cin; T.Ntot = Ntot; T.K = K; T.DIL = DIL;
   T.TN = Ntot % 128 == 0 ? 128 : (Ntot % 64 == 0 ? 64 : 32);   // widest column tile that divides the row
-  // the wide kernel stages 16 input channels at a time, the narrow ones 32; halo tile = 2 * 25 rows at most
-  if (Ntot % 32 || Cin % (T.TN == 128 ? 16 : 32) || (K - 1) / 2 * DIL > 25) { T.TN = 0; return T; }
+  // the kernels stage 32 input channels at a time (128-byte rows for the activation TMA); halo tile = 2 * 25 rows at most
+  if (Ntot % 32 || Cin % 32 || (K - 1) / 2 * DIL > 25) { T.TN = 0; return T; }
   T.w_off = round_up(c->h_tcw.size(), 64);
   const int slot = 16 * T.TN;   // floats: 2 (hi|lo) x 2 (column blocks) x TN x 8 halfs
   c->h_tcw.resize(T.w_off + (size_t)(Ntot / T.TN) * (Cin / 16) * K * slot, 0.f);
@@ -660,11 +660,11 @@ static int finalize(ovc_ctx* c) {
   CK(cudaMemcpy(c->d_tcw, c->h_tcw.data(), c->h_tcw.size() * sizeof(float), cudaMemcpyHostToDevice));
   c->h_tcw.clear();
   c->h_tcw.shrink_to_fit();
-  CK((cudaFuncSetAttribute(tcconv_wide_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcwCfg<1, 2>::SMEM_BYTES)));
-  CK((cudaFuncSetAttribute(tcconv_wide_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcwCfg<1, 1>::SMEM_BYTES)));
-  CK((cudaFuncSetAttribute(tcconv_wide_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcwCfg<2, 1>::SMEM_BYTES)));
-  CK(cudaFuncSetAttribute(tcconv_narrow_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<64>::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tcconv_narrow_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<32>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcwCfg<1>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcwCfg<2>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<128>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<64>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<32>::SMEM_BYTES));
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
   CK(cudaMalloc(&c->d_cond_wrow, wrow.size() * sizeof(int)));
@@ -858,38 +858,23 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   a.passes = r.c->precision == 2 ? 1 : 3;
   if (T.TN == 0) return fail(OVC_ERR_INVALID, "conv %d -> %d (k %d, dilation %d) does not fit the tensor-core kernels", T.Cin, T.Ntot, T.K, T.DIL);
   TRY(prof_begin(r));
-  if (T.TN == 128) {
-    // wide_variant 0: 128-step tiles, two CTAs per SM, 2-CTA clusters multicasting the weight stream;
-    //              1: 256-step tiles, one CTA per SM; 2: as 0 without clusters
-    const int wv = r.c->wide_variant;
-    const int MT = wv == 1 ? 2 : 1, CL = wv == 0 ? 2 : 1;
+  const int wv = r.c->wide_variant;
+  if (T.TN == 128 && wv != 0) {
+    // A/B alternatives of the 128-column layers: 1 = 256-step tiles, one CTA per SM; 2 = 128-step tiles, two CTAs per SM
+    const int MT = wv == 1 ? 2 : 1;
     dim3 grid((t_len + MT * 128 - 1) / (MT * 128), T.Ntot / 128, r.B);
-    grid.x = (grid.x + CL - 1) / CL * CL;   // whole clusters along time
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.stream = r.st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (wv == 0) {
-      cfg.blockDim = dim3(TcwCfg<1, 2>::THREADS); cfg.dynamicSmemBytes = TcwCfg<1, 2>::SMEM_BYTES;
-      CK((cudaLaunchKernelEx(&cfg, tcconv_wide_kernel<1, 2>, a)));
-    } else if (wv == 1) {
-      cfg.blockDim = dim3(TcwCfg<2, 1>::THREADS); cfg.dynamicSmemBytes = TcwCfg<2, 1>::SMEM_BYTES;
-      CK((cudaLaunchKernelEx(&cfg, tcconv_wide_kernel<2, 1>, a)));
-    } else {
-      cfg.blockDim = dim3(TcwCfg<1, 1>::THREADS); cfg.dynamicSmemBytes = TcwCfg<1, 1>::SMEM_BYTES;
-      CK((cudaLaunchKernelEx(&cfg, tcconv_wide_kernel<1, 1>, a)));
-    }
+    if (wv == 1) tcconv_wide_kernel<2><<<grid, TcwCfg<2>::THREADS, TcwCfg<2>::SMEM_BYTES, r.st>>>(a);
+    else tcconv_wide_kernel<1><<<grid, TcwCfg<1>::THREADS, TcwCfg<1>::SMEM_BYTES, r.st>>>(a);
   } else {
-    // one CTA per SM walks the (utterance, tile) list; column tiles (if any) on grid.y
-    const int steps = (T.TN == 64 ? TcnCfg<64>::MT : TcnCfg<32>::MT) * 128;
+    // persistent: one CTA per SM walks the (utterance, tile) list; column tiles (if any) on grid.y
+    const int steps = (T.TN == 128 ? TcnCfg<128>::MT : TcnCfg<64>::MT) * 128;
     const int n_tt = (t_len + steps - 1) / steps, total = n_tt * r.B;
     const int ncol = T.Ntot / T.TN;
     const int per_col = std::max(1, r.c->sm_count / ncol);
     dim3 pg((unsigned)std::min(total, per_col), ncol, 1);
-    if (T.TN == 64) tcconv_narrow_kernel<64><<<pg, TCN_THREADS, TcnCfg<64>::SMEM_BYTES, r.st>>>(a, n_tt, total);
-    else tcconv_narrow_kernel<32><<<pg, TCN_THREADS, TcnCfg<32>::SMEM_BYTES, r.st>>>(a, n_tt, total);
+    if (T.TN == 128) tcconv_kernel<128><<<pg, TCN_THREADS, TcnCfg<128>::SMEM_BYTES, r.st>>>(a, n_tt, total);
+    else if (T.TN == 64) tcconv_kernel<64><<<pg, TCN_THREADS, TcnCfg<64>::SMEM_BYTES, r.st>>>(a, n_tt, total);
+    else tcconv_kernel<32><<<pg, TCN_THREADS, TcnCfg<32>::SMEM_BYTES, r.st>>>(a, n_tt, total);
   }
   CK(cudaGetLastError());
   r.c->launches++;

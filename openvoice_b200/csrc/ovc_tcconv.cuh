@@ -15,8 +15,9 @@
 //
 // K-major, no-swizzle operand tiles (see ovc_tc.cuh): a convolution tap is a 16-byte-per-row shift of the A
 // descriptor's start address, so all taps (any dilation) read ONE staged halo tile.  Two kernels:
-//   tcconv_wide_kernel<MT, CL>  TN = 128 output columns per CTA, MT tiles of 128 time steps, one tile set per CTA
-//   tcconv_narrow_kernel<TN>    TN = 64 / 32, persistent: one CTA per SM walks the (utterance, tile) list
+//   tcconv_kernel<TN>        TN = 128 / 64 / 32 output columns, persistent: one CTA per SM walks the (utterance, tile)
+//                            list, activations staged by TMA, epilogue of tile i under the MMAs of tile i+1
+//   tcconv_wide_kernel<MT>   TN = 128, one tile set (MT x 128 steps) per CTA (kept as the A/B alternative)
 #pragma once
 #include "ovc_conv.cuh"
 #include "ovc_tc.cuh"
@@ -38,28 +39,6 @@ struct TcConvArgs {
   int passes;   // 3: split precision (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo); 1: single-pass fp16 (11-bit operands, like cuDNN's TF32 default)
 };
 
-// cluster helpers (CL-CTA clusters share every weight slot: each CTA fetches 1/CL of it and multicasts it to all)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -80,7 +59,7 @@ __device__ __forceinline__ void tc_item(int i, int& row, int& kc) {
 // the next TN (low-order accumulator).
 template <int TN, int MT>
 __device__ __forceinline__ void tc_epilogue(const TcConvArgs& a, uint32_t acc, int b, int t0, int n0, int lim, int warp, int lane,
-                                            int mt_lo, int mt_hi) {
+                                            int mt_lo, int mt_hi, int c_lo = 0, int c_hi = TN) {
   const int lane_base = (warp & 3) * 32;
   float* yb = a.y + (size_t)b * a.y_bs;
   const float* rb = a.r ? a.r + (size_t)b * a.y_bs : nullptr;
@@ -94,7 +73,7 @@ __device__ __forceinline__ void tc_epilogue(const TcConvArgs& a, uint32_t acc, i
     float* yp = yb + (size_t)t * a.y_ld + n0;
     const float* rp = rb ? rb + (size_t)t * a.y_ld + n0 : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < TN; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
       // everything with latency is issued first: the residual / accumulate loads, then both TMEM reads
       float4 rq[8], yq[8];
       if (a.epi == 0) {
@@ -194,15 +173,16 @@ __device__ __forceinline__ void tc_epilogue(const TcConvArgs& a, uint32_t acc, i
 // ---------------------------------------------------------------------------------------------------------
 // tcconv_wide_kernel: TN = 128 output columns, one tile set (MT x 128 steps) per CTA.
 //   MT = 1: 256 TMEM columns and ~109 KB of shared memory per CTA -> TWO CTAs per SM, so one CTA's prologue /
-//           epilogue overlaps the other's MMAs; CL = 2 clusters halve the L2 weight reads (each CTA fetches half
-//           of every weight slot and multicasts it), which is what re-streaming the layer per 128 steps costs.
+//           epilogue overlaps the other's MMAs (the layer's weights are re-streamed per 128 steps).
 //   MT = 2: all 512 TMEM columns, one CTA per SM, weights streamed once per 256 steps, serial epilogue.
+// (A 2-CTA-cluster variant that multicast the weight stream was measured in round 2: no faster, and wrong results
+// whenever both CTAs of a cluster were active -- removed.)
 // Warp roles: warp 0 TMA weight producer; warp 1 (and 6 when MT >= 2) one MMA-issuing thread each; warps 2..5
 // A producers (cp.async raw rows RAWD chunks ahead -> lrelu -> hi/lo fp16 split -> operand layout), then epilogue.
 // ---------------------------------------------------------------------------------------------------------
-template <int MT_, int CL_>
+template <int MT_>
 struct TcwCfg {
-  static constexpr int TN = 128, MT = MT_, CL = CL_;
+  static constexpr int TN = 128, MT = MT_;
   static constexpr int KCH = 16, NKC = KCH / 8, KS = KCH / 16;    // channels per A stage
   static constexpr int NISS = MT >= 2 ? 2 : 1;                    // MMA-issuing threads
   static constexpr int THREADS = NISS == 2 ? 224 : 192;
@@ -218,9 +198,9 @@ struct TcwCfg {
   static constexpr int MINB = MT == 1 ? 2 : 1;
 };
 
-template <int MT, int CL>
-__global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB) tcconv_wide_kernel(const TcConvArgs a) {
-  using Cfg = TcwCfg<MT, CL>;
+template <int MT>
+__global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_wide_kernel(const TcConvArgs a) {
+  using Cfg = TcwCfg<MT>;
   constexpr int TN = Cfg::TN, NABUF = Cfg::NABUF, SLOTS = Cfg::SLOTS, ROWS = Cfg::ROWS, NKC = Cfg::NKC, NISS = Cfg::NISS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -236,10 +216,7 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
   const int t0 = blockIdx.x * (MT * 128);
   const int n0 = blockIdx.y * TN;
   const int lim = (a.lens ? (int)min((long long)a.tmax, a.lens[b]) : a.tmax) * a.mul;
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
-  if (t0 - (int)crank * (MT * 128) >= lim) return;   // the whole cluster lies past the utterance (cluster-uniform)
-  const bool active = t0 < lim;                       // a padding CTA still takes part in the weight multicast
-  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
+  if (t0 >= lim) return;   // the tile lies past the utterance
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = (a.K - 1) / 2 * a.DIL;
@@ -248,14 +225,13 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
 
   if (tid == 0) {
     for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], NISS); }
-    for (int i = 0; i < SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL * NISS); }
+    for (int i = 0; i < SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NISS); }
     mbar_init(acc_full, NISS);
     fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc::fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // every CTA's barriers exist before any remote arrive / multicast
   tc::fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
@@ -263,15 +239,13 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
     // ------------------------------------------------------------ weight producer (TMA bulk)
     if (lane == 0) {
       const unsigned char* wp = reinterpret_cast<const unsigned char*>(a.w) + (size_t)blockIdx.y * n_slots * Cfg::SLOT_BYTES;
-      constexpr uint32_t BYTES = Cfg::SLOT_BYTES, PART = BYTES / CL;
+      constexpr uint32_t BYTES = Cfg::SLOT_BYTES;
       int slot = 0;
       uint32_t phase = 1;   // the first pass over the ring finds every slot free
       for (int it = 0; it < n_slots; ++it) {
         mbar_wait(&b_empty[slot], phase);
         mbar_expect_tx(&b_full[slot], BYTES);
-        unsigned char* dst = bring + slot * Cfg::SLOT_BYTES;
-        if (CL == 1) tma_bulk_g2s(dst, wp, BYTES, &b_full[slot]);
-        else tma_bulk_g2s_mcast(dst + crank * PART, wp + crank * PART, PART, &b_full[slot], CMASK);
+        tma_bulk_g2s(bring + slot * Cfg::SLOT_BYTES, wp, BYTES, &b_full[slot]);
         wp += Cfg::SLOT_BYTES;
         if (++slot == SLOTS) { slot = 0; phase ^= 1; }
       }
@@ -296,7 +270,7 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
       bool first = true;
       for (int q = 0; q < nq; ++q) {
         const int buf = q % NABUF;
-        if (active) mbar_wait(&a_full[buf], (q / NABUF) & 1);
+        mbar_wait(&a_full[buf], (q / NABUF) & 1);
         tc::fence_after();
         for (int j = 0; j < Cfg::KS; ++j) {
           uint64_t a_cur = a_proto + ((tc::smem_addr(abuf + buf * Cfg::A_BUF_BYTES) + 2 * j * LBO_A) >> 4);
@@ -304,13 +278,10 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
             mbar_wait(&b_full[slot], bphase);
             tc::fence_after();
             const uint64_t b_slot = b_ring + (uint32_t)slot * SLOT16;
-            if (active) {
-              // output step (t0 + mt*128 + i) reads staged row (mt*128 + i + tap*DIL): the halo tile starts at t0 - H
-              OVC_TC_ISSUE_MMAS(tmem_d)
-            }
+            // output step (t0 + mt*128 + i) reads staged row (mt*128 + i + tap*DIL): the halo tile starts at t0 - H
+            OVC_TC_ISSUE_MMAS(tmem_d)
             first = false;
-            if (CL == 1) tc::mma_commit(&b_empty[slot]);       // slot reusable once these MMAs have read it
-            else mma_commit_mcast(&b_empty[slot], CMASK);      // ... in every CTA of the cluster
+            tc::mma_commit(&b_empty[slot]);       // slot reusable once these MMAs have read it
             a_cur += dil;
             if (++slot == SLOTS) { slot = 0; bphase ^= 1; }
           }
@@ -319,7 +290,7 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
       }
       tc::mma_commit(acc_full);
     }
-  } else if (active && warp >= 2 && warp <= 5) {
+  } else if (warp >= 2 && warp <= 5) {
     // ------------------------------------------------------------ A producers, then epilogue
     const int pt = tid - 64;                                   // 0..127
     const float* xb = a.x + (size_t)b * a.x_bs;
@@ -374,62 +345,76 @@ __global__ void __launch_bounds__(TcwCfg<MT, CL>::THREADS, TcwCfg<MT, CL>::MINB)
   }
   tc::fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // peers may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) tc::tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// tcconv_narrow_kernel: persistent variant for the narrow layers (TN = 32 / 64 output columns per CTA).
-// Per tile these layers have only a few microseconds of MMA work and are HBM-bound at layer granularity, so a
-// one-tile-per-CTA kernel is dominated by fixed costs (barrier init, TMEM allocation, first-load latency, a serial
-// epilogue).  Here one CTA per SM loops over tiles: barriers / TMEM live for the whole launch, the layer's weights
-// stay resident in shared memory when they fit (C = 32: <= 44 KB; C = 64, k = 3: 48 KB; otherwise the ring streams
-// them per tile), A staging (32 channels per stage) runs ahead across tile boundaries, and the epilogue of tile i
-// (its own 8 warps, second TMEM accumulator set) overlaps the MMAs of tile i+1.
-// Warps: 0 TMA, 1-2 MMA issuers, 3-6 A producers, 7-14 epilogue.
+// tcconv_kernel<TN>: persistent split-precision conv, TN = 128 / 64 / 32 output columns per CTA.
+// One CTA per SM loops over tiles (TN = 128: 128 steps, else 256): barriers / TMEM live for the whole launch, the
+// layer's weights stay resident in shared memory when they fit (C = 32: <= 44 KB; C = 64, k = 3: 48 KB; otherwise a
+// ring streams them per tile), and every stage runs ahead across tile boundaries:
+//   warp 15     activation TMA: a chunk of a halo tile = rows x 32 channels = one 128-byte run per row of the
+//               channels-last tensor; the 32 lanes issue one cp.async.bulk per row (mbarrier complete_tx) into a raw
+//               fp32 stage, NRAW chunks ahead -- the copy engine, not registers, holds the bytes in flight (the narrow
+//               layers are HBM-bound: a whole tile must be in flight per SM to cover the latency)
+//   warps 3-6   converters: raw stage -> lrelu -> fp16 hi/lo split -> operand layout; rows outside the utterance
+//               become zeros here (zero padding, x_mask and the ragged batch in one rule)
+//   warp 0      weight TMA; warps 1-2 one MMA-issuing thread each (TN = 128: one)
+//   warps 7-14  epilogue of tile i (second TMEM accumulator set) while the MMAs of tile i+1 run
+// Raw rows are 144 bytes apart and operand column blocks ROWS = 2 (mod 8) rows apart: both sides of the conversion
+// are shared-memory bank-conflict free.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TCN_THREADS = 480;
+constexpr int TCN_THREADS = 512;
 
 template <int TN>
 struct TcnCfg {
-  static constexpr int MT = TN == 32 ? 4 : 2;                     // 2 sets x (main + low-order) x MT x TN = 512 TMEM columns
+  static constexpr int MT = TN == 128 ? 1 : 2;                    // 2 sets x MT x (main + low-order) x TN <= 512 TMEM columns
+  static constexpr int NISS = MT >= 2 ? 2 : 1;
   static constexpr int KCH = 32, NKC = KCH / 8, KS = KCH / 16;
-  static constexpr int ROWS = MT * 128 + 64;
-  static constexpr int NABUF = TN == 32 ? 2 : 3;
-  static constexpr int RING = TN == 32 ? 22 : 16;                 // weight slots: 44 KB (TN 32) / 64 KB (TN 64)
+  static constexpr int ROWS = MT * 128 + 66;                      // = 2 (mod 8)
+  static constexpr int RAW_ROWS = MT * 128 + 56;                  // tile + 2 * 25 halo, rounded up to 8
+  static constexpr int RAW_LD = 144;                              // bytes between raw rows (128 of data)
+  static constexpr int NABUF = 2;
+  static constexpr int NRAW = TN == 128 ? 3 : 2;                  // raw fp32 chunk stages
+  static constexpr int RAW_STAGE_BYTES = RAW_ROWS * RAW_LD;
+  static constexpr int RING = TN == 32 ? 22 : 12;                 // weight slots: 44 KB (TN 32) / 48 KB (TN 64) / 96 KB (TN 128)
   static constexpr int A_BUF_BYTES = 2 * NKC * ROWS * 16;
   static constexpr int SLOT_BYTES = 2 * 2 * TN * 16;
-  static constexpr size_t SMEM_BYTES = 1024 + NABUF * A_BUF_BYTES + RING * SLOT_BYTES;
-  static constexpr uint32_t TMEM_COLS = 2 * 2 * MT * TN;          // = 512
+  static constexpr size_t SMEM_BYTES = 1024 + NABUF * A_BUF_BYTES + RING * SLOT_BYTES + NRAW * RAW_STAGE_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * 2 * MT * TN;          // 512 (TN 128, 64) / 256 (TN 32)
 };
 
 template <int TN>
-__global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcConvArgs a, int n_tt, int total) {
+__global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs a, int n_tt, int total) {
   using Cfg = TcnCfg<TN>;
-  constexpr int MT = Cfg::MT, ROWS = Cfg::ROWS, NABUF = Cfg::NABUF, RING = Cfg::RING, NKC = Cfg::NKC;
+  constexpr int MT = Cfg::MT, ROWS = Cfg::ROWS, NABUF = Cfg::NABUF, RING = Cfg::RING, NKC = Cfg::NKC, NRAW = Cfg::NRAW,
+                NISS = Cfg::NISS, RAW_LD = Cfg::RAW_LD;
   constexpr uint32_t SET_COLS = 2 * MT * TN;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* a_full = bars, *a_empty = bars + NABUF, *b_full = bars + 2 * NABUF, *b_empty = b_full + RING,
-            *acc_full = b_empty + RING, *acc_empty = acc_full + 2;
-  static_assert((2 * NABUF + 2 * RING + 4) * 8 + 8 <= 1024, "barrier area");
-  static_assert(Cfg::TMEM_COLS == 512, "TMEM budget");
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+            *acc_full = b_empty + RING, *acc_empty = acc_full + 2, *raw_full = acc_empty + 2, *raw_empty = raw_full + NRAW;
+  static_assert((2 * NABUF + 2 * RING + 4 + 2 * NRAW) * 8 + 8 <= 1024, "barrier area");
+  static_assert(Cfg::SMEM_BYTES <= 232448, "shared memory budget");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + NRAW);
   unsigned char* abuf = smem_raw + 1024;
   unsigned char* bring = abuf + NABUF * Cfg::A_BUF_BYTES;
+  unsigned char* raw = bring + RING * Cfg::SLOT_BYTES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.y * TN;
   const int H = (a.K - 1) / 2 * a.DIL;
+  const int rows8 = (MT * 128 + 2 * H + 7) & ~7;
   const int nq = a.Cin / Cfg::KCH;
   const int n_slots = (a.Cin / 16) * a.K;
   const bool resident = n_slots <= RING;
   constexpr uint32_t BYTES = Cfg::SLOT_BYTES;
 
   if (tid == 0) {
-    for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 2); }
-    for (int i = 0; i < RING; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], NISS); }
+    for (int i = 0; i < RING; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NISS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], NISS); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < NRAW; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 128); }
     fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -468,10 +453,28 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcC
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ------------------------------------------------------------ MMA issuers (each owns half of the MMA tiles)
+  } else if (warp == 15) {
+    // ------------------------------------------------------------ activation chunks: one 128-byte bulk copy per row
+    int st = 0;
+    uint32_t phase = 1;   // the first pass finds every raw stage free
+    TCN_FOR_TILES
+      const int lo = t0 - H, hi = lo + rows8;
+      const int vlo = lo < 0 ? 0 : lo, vhi = hi < lim ? hi : lim;   // rows outside [0, lim) are zeroed by the converters
+      const int nrows = vhi - vlo;
+      const float* src0 = a.x + (size_t)b * a.x_bs + (size_t)vlo * a.Cin;
+      for (int q = 0; q < nq; ++q) {
+        mbar_wait(&raw_empty[st], phase);
+        unsigned char* dst0 = raw + st * Cfg::RAW_STAGE_BYTES + (vlo - lo) * RAW_LD;
+        if (lane == 0) mbar_expect_tx(&raw_full[st], (uint32_t)nrows * 128u);
+        for (int r = lane; r < nrows; r += 32)
+          tma_bulk_g2s(dst0 + r * RAW_LD, src0 + (size_t)r * a.Cin + q * Cfg::KCH, 128u, &raw_full[st]);
+        if (++st == NRAW) { st = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 || (NISS == 2 && warp == 2)) {
+    // ------------------------------------------------------------ MMA issuers (one thread each)
     if (lane == 0) {
-      const int mt_lo = (warp - 1) * (MT / 2), mt_hi = mt_lo + MT / 2;
+      const int mt_lo = (warp - 1) * (MT / NISS), mt_hi = mt_lo + MT / NISS;
       const uint32_t idesc1 = tc::make_idesc_f16(128, TN), idesc2 = tc::make_idesc_f16(128, 2 * TN);
       constexpr uint32_t LBO_A = ROWS * 16, LBO_B = 2 * TN * 16, SBO = 128;
       constexpr uint32_t A_LO16 = (NKC * ROWS * 16) >> 4, SLOT16 = Cfg::SLOT_BYTES >> 4;
@@ -515,63 +518,53 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_narrow_kernel(const TcC
       }
     }
   } else if (warp >= 3 && warp <= 6) {
-    // ------------------------------------------------------------ A producers (run ahead across tiles)
+    // ------------------------------------------------------------ converters (run ahead across tiles)
     const int pt = tid - 96;
-    const int rows8 = (MT * 128 + 2 * H + 7) & ~7;
-    const int items = rows8 * NKC;
-    int buf = 0;
-    uint32_t ephase = 1;
+    const int items = rows8 * NKC;            // item i = (row i / 4, column block i % 4): 32 bytes of one raw row
+    int buf = 0, st = 0;
+    uint32_t ephase = 1, rphase = 0;
     TCN_FOR_TILES
-      const float* xb = a.x + (size_t)b * a.x_bs;
+      (void)b;
       for (int q = 0; q < nq; ++q) {
+        mbar_wait(&raw_full[st], rphase);
         mbar_wait(&a_empty[buf], ephase);
+        const unsigned char* rsrc = raw + st * Cfg::RAW_STAGE_BYTES;
         unsigned char* ah = abuf + buf * Cfg::A_BUF_BYTES;
         unsigned char* al = ah + NKC * ROWS * 16;
-        constexpr int PB = 5;   // loads of PB items (32 bytes each) in flight per thread
-        for (int i0 = pt; i0 < items; i0 += 128 * PB) {
-          float4 v0[PB], v1[PB];
-#pragma unroll
-          for (int u = 0; u < PB; ++u) {
-            const int i = i0 + 128 * u;
-            int row, kc;
-            tc_item<NKC>(i, row, kc);
-            const int t = t0 - H + row;
-            v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            v1[u] = v0[u];
-            if (i < items && t >= 0 && t < lim) {
-              const float4* src = reinterpret_cast<const float4*>(xb + (size_t)t * a.Cin + q * Cfg::KCH + kc * 8);
-              v0[u] = src[0];
-              v1[u] = src[1];
-            }
+        for (int i = pt; i < items; i += 128) {
+          const int row = i >> 2, kc = i & 3;
+          const int t = t0 - H + row;
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          if (t >= 0 && t < lim) {
+            const float4* src = reinterpret_cast<const float4*>(rsrc + row * RAW_LD + kc * 32);
+            v0 = src[0];
+            v1 = src[1];
           }
-#pragma unroll
-          for (int u = 0; u < PB; ++u) {
-            const int i = i0 + 128 * u;
-            if (i >= items) break;
-            int row, kc;
-            tc_item<NKC>(i, row, kc);
-            uint4 hi, lo;
-            tc::split_f16x8(v0[u], v1[u], a.slope, hi, lo);
-            *reinterpret_cast<uint4*>(ah + (kc * ROWS + row) * 16) = hi;
-            *reinterpret_cast<uint4*>(al + (kc * ROWS + row) * 16) = lo;
-          }
+          uint4 hi, lo;
+          tc::split_f16x8(v0, v1, a.slope, hi, lo);
+          *reinterpret_cast<uint4*>(ah + (kc * ROWS + row) * 16) = hi;
+          *reinterpret_cast<uint4*>(al + (kc * ROWS + row) * 16) = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&a_full[buf]);
+        mbar_arrive(&raw_empty[st]);            // this thread has read everything it needs from the raw stage
         if (++buf == NABUF) { buf = 0; ephase ^= 1; }
+        if (++st == NRAW) { st = 0; rphase ^= 1; }
       }
     }
-  } else if (warp >= 7) {
+  } else if (warp >= 7 && warp <= 14) {
     // ------------------------------------------------------------ epilogue (overlaps the next tile's MMAs)
-    // warps 7..10 take MMA tiles [0, MT/2), warps 11..14 the rest; each covers the TMEM lane quadrant warp % 4
+    // each warp covers the TMEM lane quadrant warp % 4; warps 7..10 / 11..14 split the MMA tiles (MT = 2) or the
+    // columns (MT = 1) of the CTA tile between them
     const int half = (warp - 7) >> 2;
-    const int mt_lo = half * (MT / 2), mt_hi = mt_lo + MT / 2;
+    const int mt_lo = MT == 2 ? half : 0, mt_hi = MT == 2 ? half + 1 : 1;
+    const int c_lo = MT == 2 ? 0 : half * (TN / 2), c_hi = MT == 2 ? TN : c_lo + TN / 2;
     int n = 0;
     TCN_FOR_TILES
       const int set = n & 1;
       mbar_wait(&acc_full[set], (n >> 1) & 1);
       tc::fence_after();
-      tc_epilogue<TN, MT>(a, tmem_d + set * SET_COLS, b, t0, n0, lim, warp, lane, mt_lo, mt_hi);
+      tc_epilogue<TN, MT>(a, tmem_d + set * SET_COLS, b, t0, n0, lim, warp, lane, mt_lo, mt_hi, c_lo, c_hi);
       tc::fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[set]);

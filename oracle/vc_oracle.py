@@ -391,7 +391,7 @@ def spectrogram(y: torch.Tensor, n_fft: int = 1024, hop: int = 256, win: int = 1
     (n_fft-hop)/2 both sides, periodic hann, centre=False, sqrt(re^2+im^2+1e-6)."""
     p = int((n_fft - hop) / 2)
     yp = F.pad(y.unsqueeze(1), (p, p), mode="reflect").squeeze(1)
-    window = torch.hann_window(win, dtype=y.dtype)
+    window = torch.hann_window(win, dtype=y.dtype, device=y.device)
     s = torch.stft(yp, n_fft, hop_length=hop, win_length=win, window=window, center=False,
                    normalized=False, onesided=True, return_complex=True)
     s = torch.view_as_real(s)

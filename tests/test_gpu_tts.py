@@ -67,11 +67,11 @@ def test_text_side_matches_reference(name, tts):
     print(name, {k: float(v) for k, v in err.items()})
     for k in ("x", "m_p", "logs_p", "logw_dp"):
         assert err[k] < 1e-4, (k, err)
-    assert err["logw_sdp"] < 5e-4, err          # three spline inverses amplify the conditioning error
+    assert err["logw_sdp"] < 1e-4, err          # three spline inverses amplify the conditioning error (measured <= 6e-5)
     assert np.array_equal(w_ceil.cpu().numpy(), d["w_ceil"])
     assert np.array_equal(yl.cpu().numpy(), d["y_lengths"])
     ref_logw = (d["logw_sdp"] * c["sdp_ratio"] + d["logw_dp"] * (1 - c["sdp_ratio"]))[:, 0] * mask
-    assert np.abs(logw.cpu().numpy() - ref_logw).max() < 5e-4
+    assert np.abs(logw.cpu().numpy() - ref_logw).max() < 1e-4
 
 
 @pytest.mark.parametrize("precision", ["fp32", "f16x3"])
@@ -227,13 +227,13 @@ def test_one_token_and_very_long_text(tts):
         got = w_ceil.cpu().numpy()
         e_logw = np.abs(logw.cpu().numpy() - (lw * mask)[:, 0].numpy())
         print("long text", (B, Tn), "logw err max", float(e_logw.max()), "n > 5e-4:", int((e_logw > 5e-4).sum()))
-        # the spline inverse is ill-conditioned where a bin's derivative sits at its 1e-3 floor (slope of the inverse up
-        # to 1e3): a 2e-5 error on x becomes up to ~5e-3 on a handful of tokens (tools/diag_tts_long.py: 4 of 300, 25 of
-        # 2200 above 5e-4, none above 1e-2; positions random, not tile-aligned).  Gate: 99 % within 5e-4, all within 5e-3.
-        assert e_logw.max() < 5e-3 and (e_logw > 5e-4).sum() <= max(1, int(0.01 * e_logw.size)), \
-            (B, Tn, float(e_logw.max()), int((e_logw > 5e-4).sum()))
-        diff = np.abs(got - ref)
-        assert diff.max() <= 1 and (diff > 0).sum() <= max(1, int(0.002 * ref.size)), (B, Tn, int((diff > 0).sum()))
+        # The whole duration chain (SDP pre / DDSConv 1x1 / proj, DP convs) runs in plain fp32 on the CUDA cores, the
+        # text encoder's projections in split-precision fp16: x agrees with the oracle to ~5e-6, so even where the spline
+        # inverse is ill-conditioned (a bin's derivative at its 1e-3 floor: inverse slope up to 1e3) logw stays within
+        # 5e-4 (measured 1.4e-4 at T = 1500; the fp32 oracle itself sits 5e-4 from an fp64 evaluation there) and the
+        # INTEGER durations are exact.
+        assert e_logw.max() < 5e-4, (B, Tn, float(e_logw.max()))
+        assert np.array_equal(got, ref), (B, Tn, int((got != ref).sum()))
         if Tn == 1:
             o, _, y_mask, _ = tts.infer(tokens, lengths, sid=sid, noise_w=noise_w, noise_scale=0.5, noise_scale_w=0.6, seed=1)
             torch.cuda.synchronize()
