@@ -182,10 +182,13 @@ OVC_API int ovc_set_precision(ovc_ctx* ctx, int mode);
  *                         128-step tile per CTA, two CTAs per SM
  *   OVC_OPT_TTS_SIMPLE    1: one-thread-per-element text-side kernels (the CPU-checked element functions) instead of
  *                         the warp-cooperative LayerNorm / fused attention
+ *   OVC_OPT_ACT_TMA       1 (default): the persistent conv kernel receives its activation tiles by tensor-map TMA;
+ *                         0: its converter warps load them from global memory
  *   OVC_OPT_GRAPH         1 (default): replay the launch sequence of a repeated (shape, buffers) call from a CUDA graph */
 #define OVC_OPT_WIDE_VARIANT 1
 #define OVC_OPT_TTS_SIMPLE 2
 #define OVC_OPT_GRAPH 3
+#define OVC_OPT_ACT_TMA 4
 OVC_API int ovc_set_option(ovc_ctx* ctx, int key, int value);
 
 /* Number of kernels the last ovc_voice_conversion / ovc_convert_waveform call launched. */

@@ -151,8 +151,10 @@ class NativeConverter:
         self.handle = h
         self.device_index = int(device_index)
         self.finalized = False
-        if os.environ.get("OVC_WIDE_VARIANT"):      # tuning experiments: tiling of the 128-column tensor-core kernel
+        if os.environ.get("OVC_WIDE_VARIANT"):      # tuning experiments: kernel of the 128-column tensor-core layers
             self.set_option("wide_variant", int(os.environ["OVC_WIDE_VARIANT"]))
+        if os.environ.get("OVC_ACT_TMA"):
+            self.set_option("act_tma", int(os.environ["OVC_ACT_TMA"]))
 
     def close(self):
         if getattr(self, "handle", None):
@@ -193,8 +195,8 @@ class NativeConverter:
         self.precision = mode
 
     def set_option(self, key: str, value: int):
-        """Tuning switches of include/ovc.h: 'wide_variant' (0/1/2), 'tts_simple' (0/1), 'graph' (0/1)."""
-        k = {"wide_variant": 1, "tts_simple": 2, "graph": 3}[key]
+        """Tuning switches of include/ovc.h: 'wide_variant' (0/1/2), 'tts_simple' (0/1), 'graph' (0/1), 'act_tma' (0/1)."""
+        k = {"wide_variant": 1, "tts_simple": 2, "graph": 3, "act_tma": 4}[key]
         _check(self.lib, self.lib.ovc_set_option(self.handle, k, int(value)), "ovc_set_option")
 
     # ---- hot path --------------------------------------------------------------------------

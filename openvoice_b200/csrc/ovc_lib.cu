@@ -60,6 +60,22 @@ struct DeviceGuard {
                   __LINE__);                                                                      \
   } while (0)
 
+// cuTensorMapEncodeTiled, resolved through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
 static const VariantInfo kInfo[V_COUNT] = {
 #define X(name, K, D, WM, WN, CI, EPI, NG, XA)                                                    \
   {#name, K, D, 32 * WM, 64 * WN, CI, EPI, 32 * WM * WN, ConvCfg<K, D, WM, WN, CI, EPI, NG, XA>::SMEM_BYTES},
@@ -173,6 +189,7 @@ struct ovc_ctx {
   std::vector<float> h_tcw;
   int precision = 0;           // 0: fp32 FFMA everywhere; 1: 3xFP16 split-precision tcgen05 convs; 2: single-pass fp16
   int wide_variant = 0;        // tiling of the 128-column tensor-core kernel (see launch_tc)
+  bool act_tma = true;         // OVC_OPT_ACT_TMA
   bool tts_simple = false;     // OVC_OPT_TTS_SIMPLE
   bool use_graph = true;       // OVC_OPT_GRAPH
   size_t post_w_off = 0;
@@ -867,14 +884,35 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
     else tcconv_wide_kernel<1><<<grid, TcwCfg<1>::THREADS, TcwCfg<1>::SMEM_BYTES, r.st>>>(a);
   } else {
     // persistent: one CTA per SM walks the (utterance, tile) list; column tiles (if any) on grid.y
-    const int steps = (T.TN == 128 ? TcnCfg<128>::MT : TcnCfg<64>::MT) * 128;
+    const int MT = T.TN == 128 ? TcnCfg<128>::MT : TcnCfg<64>::MT;
+    const int steps = MT * 128;
     const int n_tt = (t_len + steps - 1) / steps, total = n_tt * r.B;
+    // activation chunks by tensor-map TMA: the channels-last input as a [B][rows][Cin] fp32 tensor, one box = box_rows x 32
+    // channels (128 bytes, 128-byte swizzle); rows outside the tensor are zero-filled by the copy engine
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    a.act_tma = 0;
+    if (r.c->act_tma && encode_tiled_fn()) {
+      const int rows = tcn_rows(MT, (T.K - 1) / 2 * T.DIL);
+      a.n_box = rows > 256 ? 2 : 1;
+      a.box_rows = rows / a.n_box;
+      const cuuint64_t gdim[3] = {(cuuint64_t)T.Cin, (cuuint64_t)r.P * mul, (cuuint64_t)r.B};
+      const cuuint64_t gstr[2] = {(cuuint64_t)T.Cin * 4, (cuuint64_t)a.x_bs * 4};
+      const cuuint32_t box[3] = {32, (cuuint32_t)a.box_rows, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      const CUresult cr = encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstr, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return fail(OVC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a [%d][%d][%d] activation tensor", (int)cr,
+                                          r.B, r.P * mul, T.Cin);
+      a.act_tma = 1;
+    }
     const int ncol = T.Ntot / T.TN;
     const int per_col = std::max(1, r.c->sm_count / ncol);
     dim3 pg((unsigned)std::min(total, per_col), ncol, 1);
-    if (T.TN == 128) tcconv_kernel<128><<<pg, TCN_THREADS, TcnCfg<128>::SMEM_BYTES, r.st>>>(a, n_tt, total);
-    else if (T.TN == 64) tcconv_kernel<64><<<pg, TCN_THREADS, TcnCfg<64>::SMEM_BYTES, r.st>>>(a, n_tt, total);
-    else tcconv_kernel<32><<<pg, TCN_THREADS, TcnCfg<32>::SMEM_BYTES, r.st>>>(a, n_tt, total);
+    if (T.TN == 128) tcconv_kernel<128><<<pg, TCN_THREADS, TcnCfg<128>::SMEM_BYTES, r.st>>>(a, n_tt, total, tmap);
+    else if (T.TN == 64) tcconv_kernel<64><<<pg, TCN_THREADS, TcnCfg<64>::SMEM_BYTES, r.st>>>(a, n_tt, total, tmap);
+    else tcconv_kernel<32><<<pg, TCN_THREADS, TcnCfg<32>::SMEM_BYTES, r.st>>>(a, n_tt, total, tmap);
   }
   CK(cudaGetLastError());
   r.c->launches++;
@@ -1449,6 +1487,7 @@ int ovc_set_option(ovc_ctx* c, int key, int value) {
       return OVC_OK;
     case OVC_OPT_TTS_SIMPLE: c->tts_simple = value != 0; return OVC_OK;
     case OVC_OPT_GRAPH: c->use_graph = value != 0; return OVC_OK;
+    case OVC_OPT_ACT_TMA: c->act_tma = value != 0; return OVC_OK;
     default: return fail(OVC_ERR_INVALID, "unknown option %d", key);
   }
 }

@@ -19,6 +19,8 @@
 //                            list, activations staged by TMA, epilogue of tile i under the MMAs of tile i+1
 //   tcconv_wide_kernel<MT>   TN = 128, one tile set (MT x 128 steps) per CTA (kept as the A/B alternative)
 #pragma once
+#include <cuda.h>   // CUtensorMap (the driver entry point that encodes it is resolved at run time, ovc_lib.cu)
+
 #include "ovc_conv.cuh"
 #include "ovc_tc.cuh"
 
@@ -37,7 +39,19 @@ struct TcConvArgs {
   int Cin; int Ntot; int K; int DIL;   // Ntot = output row width (C for a ResBlock conv, stride*Cout for a polyphase transposed conv)
   float slope; float scale; int accumulate;
   int passes;   // 3: split precision (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo); 1: single-pass fp16 (11-bit operands, like cuDNN's TF32 default)
+  int act_tma;  // persistent kernel: 1 = activation chunks arrive by tensor-map TMA (box_rows x 32 channels, n_box boxes per
+  int box_rows; //                    chunk), 0 = the converter warps load them from global memory themselves
+  int n_box;
 };
+
+// one box of a [B][rows][Cin] fp32 tensor -> shared memory (128-byte swizzle), completion on an mbarrier
+__device__ __forceinline__ void tma_tensor3d_g2s(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -353,16 +367,19 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
 // One CTA per SM loops over tiles (TN = 128: 128 steps, else 256): barriers / TMEM live for the whole launch, the
 // layer's weights stay resident in shared memory when they fit (C = 32: <= 44 KB; C = 64, k = 3: 48 KB; otherwise a
 // ring streams them per tile), and every stage runs ahead across tile boundaries:
-//   warp 15     activation TMA: a chunk of a halo tile = rows x 32 channels = one 128-byte run per row of the
-//               channels-last tensor; the 32 lanes issue one cp.async.bulk per row (mbarrier complete_tx) into a raw
-//               fp32 stage, NRAW chunks ahead -- the copy engine, not registers, holds the bytes in flight (the narrow
-//               layers are HBM-bound: a whole tile must be in flight per SM to cover the latency)
-//   warps 3-6   converters: raw stage -> lrelu -> fp16 hi/lo split -> operand layout; rows outside the utterance
-//               become zeros here (zero padding, x_mask and the ragged batch in one rule)
+//   warp 15     activation TMA (act_tma): a chunk of a halo tile = rows x 32 channels of the channels-last tensor is
+//               ONE tensor-map box (two when it has more than 256 rows): cp.async.bulk.tensor lands it in a raw fp32
+//               stage, 128-byte swizzled, NRAW chunks ahead, rows before the tensor's start zero-filled by the copy
+//               engine -- the copy engine, not registers, holds the bytes in flight (the narrow layers are HBM-bound:
+//               a whole tile must be in flight per SM to cover the latency).  [Measured: one 128-byte bulk copy per
+//               row instead costs ~55 cycles of TMA issue each and caps the kernel at 1.1 TB/s.]
+//   warps 3-6   converters: raw stage (or, act_tma = 0, global memory) -> lrelu -> fp16 hi/lo split -> operand
+//               layout; rows outside the utterance become zeros here (zero padding, x_mask and the ragged batch in
+//               one rule)
 //   warp 0      weight TMA; warps 1-2 one MMA-issuing thread each (TN = 128: one)
 //   warps 7-14  epilogue of tile i (second TMEM accumulator set) while the MMAs of tile i+1 run
-// Raw rows are 144 bytes apart and operand column blocks ROWS = 2 (mod 8) rows apart: both sides of the conversion
-// are shared-memory bank-conflict free.
+// The raw stage's 128-byte swizzle and the operand tiles' ROWS = 2 (mod 8) column-block pitch make both sides of
+// the conversion shared-memory bank-conflict free.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TCN_THREADS = 512;
 
@@ -372,23 +389,30 @@ struct TcnCfg {
   static constexpr int NISS = MT >= 2 ? 2 : 1;
   static constexpr int KCH = 32, NKC = KCH / 8, KS = KCH / 16;
   static constexpr int ROWS = MT * 128 + 66;                      // = 2 (mod 8)
-  static constexpr int RAW_ROWS = MT * 128 + 56;                  // tile + 2 * 25 halo, rounded up to 8
-  static constexpr int RAW_LD = 144;                              // bytes between raw rows (128 of data)
+  static constexpr int RAW_ROWS = MT == 1 ? 184 : 320;            // tile + 2 * 25 halo, rounded up to 8 (16 when two boxes)
   static constexpr int NABUF = 2;
   static constexpr int NRAW = TN == 128 ? 3 : 2;                  // raw fp32 chunk stages
-  static constexpr int RAW_STAGE_BYTES = RAW_ROWS * RAW_LD;
-  static constexpr int RING = TN == 32 ? 22 : 12;                 // weight slots: 44 KB (TN 32) / 48 KB (TN 64) / 96 KB (TN 128)
+  static constexpr int RAW_STAGE_BYTES = RAW_ROWS * 128;          // multiple of 1024: every stage keeps the swizzle phase
+  static constexpr int RING = TN == 32 ? 22 : (TN == 64 ? 12 : 13);   // weight slots: 44 KB / 48 KB / 104 KB
   static constexpr int A_BUF_BYTES = 2 * NKC * ROWS * 16;
   static constexpr int SLOT_BYTES = 2 * 2 * TN * 16;
-  static constexpr size_t SMEM_BYTES = 1024 + NABUF * A_BUF_BYTES + RING * SLOT_BYTES + NRAW * RAW_STAGE_BYTES;
+  static constexpr size_t SMEM_BYTES = 1024 + NABUF * A_BUF_BYTES + RING * SLOT_BYTES + 1024 + NRAW * RAW_STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * 2 * MT * TN;          // 512 (TN 128, 64) / 256 (TN 32)
 };
 
+// rows staged per chunk: the tile plus its halo, rounded so that one box (<= 256 rows) or two equal boxes of a
+// multiple of 8 rows cover it
+__host__ __device__ inline int tcn_rows(int mt, int H) {
+  const int r = mt * 128 + 2 * H;
+  return r <= 256 ? (r + 7) & ~7 : (r + 15) & ~15;
+}
+
 template <int TN>
-__global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs a, int n_tt, int total) {
+__global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs a, int n_tt, int total,
+                                                                const __grid_constant__ CUtensorMap tmap) {
   using Cfg = TcnCfg<TN>;
   constexpr int MT = Cfg::MT, ROWS = Cfg::ROWS, NABUF = Cfg::NABUF, RING = Cfg::RING, NKC = Cfg::NKC, NRAW = Cfg::NRAW,
-                NISS = Cfg::NISS, RAW_LD = Cfg::RAW_LD;
+                NISS = Cfg::NISS;
   constexpr uint32_t SET_COLS = 2 * MT * TN;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -399,15 +423,18 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + NRAW);
   unsigned char* abuf = smem_raw + 1024;
   unsigned char* bring = abuf + NABUF * Cfg::A_BUF_BYTES;
+  // raw stages: 1024-byte aligned in the shared window (the 128-byte swizzle is a function of address bits 4..9)
   unsigned char* raw = bring + RING * Cfg::SLOT_BYTES;
+  raw += (1024u - (smem_u32(raw) & 1023u)) & 1023u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.y * TN;
   const int H = (a.K - 1) / 2 * a.DIL;
-  const int rows8 = (MT * 128 + 2 * H + 7) & ~7;
+  const int rows8 = tcn_rows(MT, H);
   const int nq = a.Cin / Cfg::KCH;
   const int n_slots = (a.Cin / 16) * a.K;
   const bool resident = n_slots <= RING;
+  const bool act_tma = a.act_tma != 0;
   constexpr uint32_t BYTES = Cfg::SLOT_BYTES;
 
   if (tid == 0) {
@@ -454,21 +481,21 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
       }
     }
   } else if (warp == 15) {
-    // ------------------------------------------------------------ activation chunks: one 128-byte bulk copy per row
-    int st = 0;
-    uint32_t phase = 1;   // the first pass finds every raw stage free
-    TCN_FOR_TILES
-      const int lo = t0 - H, hi = lo + rows8;
-      const int vlo = lo < 0 ? 0 : lo, vhi = hi < lim ? hi : lim;   // rows outside [0, lim) are zeroed by the converters
-      const int nrows = vhi - vlo;
-      const float* src0 = a.x + (size_t)b * a.x_bs + (size_t)vlo * a.Cin;
-      for (int q = 0; q < nq; ++q) {
-        mbar_wait(&raw_empty[st], phase);
-        unsigned char* dst0 = raw + st * Cfg::RAW_STAGE_BYTES + (vlo - lo) * RAW_LD;
-        if (lane == 0) mbar_expect_tx(&raw_full[st], (uint32_t)nrows * 128u);
-        for (int r = lane; r < nrows; r += 32)
-          tma_bulk_g2s(dst0 + r * RAW_LD, src0 + (size_t)r * a.Cin + q * Cfg::KCH, 128u, &raw_full[st]);
-        if (++st == NRAW) { st = 0; phase ^= 1; }
+    // ------------------------------------------------------------ activation chunks by tensor-map TMA
+    if (lane == 0 && act_tma) {
+      int st = 0;
+      uint32_t phase = 1;   // the first pass finds every raw stage free
+      const uint32_t box_bytes = (uint32_t)a.box_rows * 128u;
+      TCN_FOR_TILES
+        (void)lim;
+        for (int q = 0; q < nq; ++q) {
+          mbar_wait(&raw_empty[st], phase);
+          mbar_expect_tx(&raw_full[st], box_bytes * (uint32_t)a.n_box);
+          unsigned char* dst = raw + st * Cfg::RAW_STAGE_BYTES;
+          for (int i = 0; i < a.n_box; ++i)   // coordinates: channel, row (may be negative: zero-filled), utterance
+            tma_tensor3d_g2s(dst + i * box_bytes, &tmap, q * Cfg::KCH, t0 - H + i * a.box_rows, b, &raw_full[st]);
+          if (++st == NRAW) { st = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1 || (NISS == 2 && warp == 2)) {
@@ -520,36 +547,69 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
   } else if (warp >= 3 && warp <= 6) {
     // ------------------------------------------------------------ converters (run ahead across tiles)
     const int pt = tid - 96;
-    const int items = rows8 * NKC;            // item i = (row i / 4, column block i % 4): 32 bytes of one raw row
+    const int items = rows8 * NKC;            // item i = (row i / 4, column block i % 4): 32 bytes of one row
     int buf = 0, st = 0;
     uint32_t ephase = 1, rphase = 0;
     TCN_FOR_TILES
-      (void)b;
+      const float* xb = a.x + (size_t)b * a.x_bs;
       for (int q = 0; q < nq; ++q) {
-        mbar_wait(&raw_full[st], rphase);
+        if (act_tma) mbar_wait(&raw_full[st], rphase);
         mbar_wait(&a_empty[buf], ephase);
-        const unsigned char* rsrc = raw + st * Cfg::RAW_STAGE_BYTES;
         unsigned char* ah = abuf + buf * Cfg::A_BUF_BYTES;
         unsigned char* al = ah + NKC * ROWS * 16;
-        for (int i = pt; i < items; i += 128) {
-          const int row = i >> 2, kc = i & 3;
-          const int t = t0 - H + row;
-          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-          if (t >= 0 && t < lim) {
-            const float4* src = reinterpret_cast<const float4*>(rsrc + row * RAW_LD + kc * 32);
-            v0 = src[0];
-            v1 = src[1];
+        if (act_tma) {
+          // raw stage, 128-byte swizzle: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4)
+          const unsigned char* rsrc = raw + st * Cfg::RAW_STAGE_BYTES;
+          for (int i = pt; i < items; i += 128) {
+            const int row = i >> 2, kc = i & 3;
+            const int t = t0 - H + row;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (t >= 0 && t < lim) {
+              const unsigned char* rr = rsrc + row * 128;
+              v0 = *reinterpret_cast<const float4*>(rr + (((2 * kc) ^ (row & 7)) << 4));
+              v1 = *reinterpret_cast<const float4*>(rr + (((2 * kc + 1) ^ (row & 7)) << 4));
+            }
+            uint4 hi, lo;
+            tc::split_f16x8(v0, v1, a.slope, hi, lo);
+            *reinterpret_cast<uint4*>(ah + (kc * ROWS + row) * 16) = hi;
+            *reinterpret_cast<uint4*>(al + (kc * ROWS + row) * 16) = lo;
           }
-          uint4 hi, lo;
-          tc::split_f16x8(v0, v1, a.slope, hi, lo);
-          *reinterpret_cast<uint4*>(ah + (kc * ROWS + row) * 16) = hi;
-          *reinterpret_cast<uint4*>(al + (kc * ROWS + row) * 16) = lo;
+        } else {
+          constexpr int PB = 5;   // items (32 bytes each) in flight per thread
+          for (int i0 = pt; i0 < items; i0 += 128 * PB) {
+            float4 v0[PB], v1[PB];
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+              const int i = i0 + 128 * u;
+              const int row = i >> 2, kc = i & 3;
+              const int t = t0 - H + row;
+              v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              v1[u] = v0[u];
+              if (i < items && t >= 0 && t < lim) {
+                const float4* src = reinterpret_cast<const float4*>(xb + (size_t)t * a.Cin + q * Cfg::KCH + kc * 8);
+                v0[u] = src[0];
+                v1[u] = src[1];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+              const int i = i0 + 128 * u;
+              if (i >= items) break;
+              const int row = i >> 2, kc = i & 3;
+              uint4 hi, lo;
+              tc::split_f16x8(v0[u], v1[u], a.slope, hi, lo);
+              *reinterpret_cast<uint4*>(ah + (kc * ROWS + row) * 16) = hi;
+              *reinterpret_cast<uint4*>(al + (kc * ROWS + row) * 16) = lo;
+            }
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&a_full[buf]);
-        mbar_arrive(&raw_empty[st]);            // this thread has read everything it needs from the raw stage
         if (++buf == NABUF) { buf = 0; ephase ^= 1; }
-        if (++st == NRAW) { st = 0; rphase ^= 1; }
+        if (act_tma) {
+          mbar_arrive(&raw_empty[st]);          // this thread has read everything it needs from the raw stage
+          if (++st == NRAW) { st = 0; rphase ^= 1; }
+        }
       }
     }
   } else if (warp >= 7 && warp <= 14) {

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "f16x3", "f16"])
     ap.add_argument("--wide-variant", type=int, default=None)
+    ap.add_argument("--act-tma", type=int, default=None)
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -41,6 +42,8 @@ def main():
     nat.set_precision(args.precision)
     if args.wide_variant is not None:
         nat.set_option("wide_variant", args.wide_variant)
+    if args.act_tma is not None:
+        nat.set_option("act_tma", args.act_tma)
     for _ in range(2):
         nat.convert_waveform(wav, wlen, g, g, tau=0.3, seed=1)
     torch.cuda.synchronize()
