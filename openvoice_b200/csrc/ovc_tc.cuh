@@ -113,6 +113,51 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// 16 TMEM lanes x 32 consecutive fp32 columns in the mma-accumulator fragment layout (16x256b.x4): thread i of the
+// warp receives, for each 8-column group g = 0..3,
+//   r[4g + 0..1] = lane (i / 4),     columns 8g + 2 (i % 4) + {0, 1}
+//   r[4g + 2..3] = lane (i / 4) + 8, columns 8g + 2 (i % 4) + {0, 1}
+// i.e. four consecutive threads hold 32 contiguous bytes (one DRAM sector) of one output row, so the global loads
+// and stores of the epilogue are sector-coalesced without a shared-memory transpose (tools/tmem_ld_probe.cu prints
+// this mapping on hardware).  `taddr` carries the first lane (a multiple of 16 inside the warp's 32-lane window).
+__device__ __forceinline__ void tmem_ld16x256_x4_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16x2(uint32_t (&r)[16], uint32_t (&q)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(q[0]),
+                 "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]), "+r"(q[9]),
+                 "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])
+               :
+               : "memory");
+}
+
+// true in exactly one lane of a converged warp (elect.sync).  The MMA-issuing warps keep their whole loop converged and
+// predicate only the tcgen05.mma / tcgen05.commit on it: operands then stay in uniform registers and ptxas emits one
+// predicated UTCHMMA instead of the per-thread ELECT / R2UR / BRA.U.ANY replay loop of a divergent `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // split an fp32 into a tf32-exact high part and the fp32 remainder (3xTF32: a*b ~ ah*bh + al*bh + ah*bl)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);

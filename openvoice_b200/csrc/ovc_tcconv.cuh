@@ -68,106 +68,156 @@ __device__ __forceinline__ void tc_item(int i, int& row, int& kc) {
   row = (i / (8 * NKC)) * 8 + (i & 7);
 }
 
-// Epilogue of MMA tiles [mt_lo, mt_hi) of one CTA tile (MT x 128 steps x TN columns): TMEM -> registers -> fused ops
-// -> global.  Warp w may read TMEM lanes [32*(w%4), +32); tile mt owns columns [2*mt*TN, +TN) (main accumulator) and
-// the next TN (low-order accumulator).
+// Epilogue of MMA tiles [mt_lo, mt_hi) x columns [c_lo, c_hi) of one CTA tile (MT x 128 steps x TN columns): TMEM ->
+// registers -> fused ops -> global.  Warp w may read TMEM lanes [32*(w%4), +32); tile mt owns columns [2*mt*TN, +TN)
+// (main accumulator) and the next TN (low-order accumulator).
+// TMEM is read in the accumulator-fragment layout (tc::tmem_ld16x256_x4_issue): one block = 16 steps x 32 columns,
+// four consecutive threads per 32-byte segment of an output row, so every global access of a warp is made of whole
+// sectors (the thread-per-row layout moved 16 bytes per sector and spilled).  Operands with DRAM latency -- the
+// residual of a ResBlock conv, the read-modify-write target of the WaveNet res/skip update -- are fetched one block
+// ahead, and those of the first block BEFORE the wait on the accumulator barrier `bar`: they arrive under the MMAs.
 template <int TN, int MT>
 __device__ __forceinline__ void tc_epilogue(const TcConvArgs& a, uint32_t acc, int b, int t0, int n0, int lim, int warp, int lane,
-                                            int mt_lo, int mt_hi, int c_lo = 0, int c_hi = TN) {
+                                            int mt_lo, int mt_hi, int c_lo, int c_hi, uint64_t* bar, uint32_t parity) {
   const int lane_base = (warp & 3) * 32;
+  const int rsub = lane >> 2, csub = (lane & 3) * 2;
   float* yb = a.y + (size_t)b * a.y_bs;
   const float* rb = a.r ? a.r + (size_t)b * a.y_bs : nullptr;
   float* sb = a.s ? a.s + (size_t)b * a.s_bs : nullptr;
   const float* bias = a.bias + (size_t)b * a.bias_bs;
   const bool two = a.passes == 3;
-#pragma unroll 1
-  for (int mt = mt_lo; mt < mt_hi; ++mt) {
-    const int t = t0 + mt * 128 + lane_base + lane;
-    const bool ok = t < lim;
-    float* yp = yb + (size_t)t * a.y_ld + n0;
-    const float* rp = rb ? rb + (size_t)t * a.y_ld + n0 : nullptr;
-#pragma unroll 1
-    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-      // everything with latency is issued first: the residual / accumulate loads, then both TMEM reads
-      float4 rq[8], yq[8];
-      if (a.epi == 0) {
-        if (ok && rp) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) rq[q] = *reinterpret_cast<const float4*>(rp + c0 + 4 * q);
-        }
-        if (ok && a.accumulate) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) yq[q] = *reinterpret_cast<const float4*>(yp + c0 + 4 * q);
-        }
-      }
-      uint32_t rm[32];
-      float v[32];
-      tc::tmem_ld32_issue(acc + ((uint32_t)lane_base << 16) + 2 * mt * TN + c0, rm);
-      tc::tmem_ld_wait(rm);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rm[i]);
-      if (two) {
-        tc::tmem_ld32_issue(acc + ((uint32_t)lane_base << 16) + (2 * mt + 1) * TN + c0, rm);
-        tc::tmem_ld_wait(rm);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(rm[i]), tc::kLoInv, v[i]);
-      }
-      if (!ok) continue;
-      if (a.epi != 0) {
-        // ---- WaveNet epilogues (modules.py:185-210), channels-last
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += bias[n0 + c0 + i];
-        const int col = n0 + c0;
-        if (a.epi == 1) {
-          // columns [0,16) of the group: tanh inputs of 16 channels, [16,32): their sigmoid partners
-          float* op = yb + (size_t)t * a.y_ld + (col >> 1);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = tanhf(v[4 * q + e]) * sigmoidf_acc(v[16 + 4 * q + e]);
-            *reinterpret_cast<float4*>(op + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-        } else {
-          const bool to_x = col < a.split;          // uniform per 32-column group (split is a multiple of 32)
-          float* op = to_x ? yb + (size_t)t * a.y_ld + col : sb + (size_t)t * a.y_ld + (col - a.split);
-          const bool add = to_x || !a.first;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (add) cur = *reinterpret_cast<const float4*>(op + 4 * q);
-            cur.x += v[4 * q]; cur.y += v[4 * q + 1]; cur.z += v[4 * q + 2]; cur.w += v[4 * q + 3];
-            *reinterpret_cast<float4*>(op + 4 * q) = cur;
-          }
-        }
-        continue;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 bq = *reinterpret_cast<const float4*>(bias + n0 + c0 + 4 * q);
-        v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
-      }
-      if (rp) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          v[4 * q] += rq[q].x; v[4 * q + 1] += rq[q].y; v[4 * q + 2] += rq[q].z; v[4 * q + 3] += rq[q].w;
-        }
-      }
-      if (a.accumulate) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          v[4 * q] = yq[q].x + v[4 * q]; v[4 * q + 1] = yq[q].y + v[4 * q + 1];
-          v[4 * q + 2] = yq[q].z + v[4 * q + 2]; v[4 * q + 3] = yq[q].w + v[4 * q + 3];
-        }
-      }
-      if (a.scale != 1.f) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= a.scale;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(yp + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  const int ncb = (c_hi - c_lo) >> 5;
+  const int nblk = (mt_hi - mt_lo) * ncb * 2;
+
+  // block k -> (MMA tile, 32-column group, 16-row half); rows a = first row of this thread, b = a + 8
+  auto geom = [&](int k, int& mt, int& c0, int& row) {
+    const int h = k & 1, q = k >> 1;
+    mt = mt_lo + q / ncb;
+    c0 = c_lo + (q % ncb) * 32;
+    row = lane_base + 16 * h + rsub;
+  };
+  // where block k's read-modify-write / residual operand lives (nullptr: none)
+  auto operand = [&](int c0, bool& add) -> const float* {
+    add = true;
+    if (a.epi == 0) return rb ? rb + n0 + c0 + csub : nullptr;
+    if (a.epi == 2) {
+      const int col = n0 + c0;
+      const bool to_x = col < a.split;          // uniform per 32-column group (split is a multiple of 32)
+      add = to_x || !a.first;
+      return to_x ? yb + col + csub : sb + (col - a.split) + csub;
     }
+    return nullptr;
+  };
+  auto prefetch = [&](int k, float2 (&q)[8]) {
+    int mt, c0, row;
+    geom(k, mt, c0, row);
+    bool add;
+    const float* src = operand(c0, add);
+    const int ta = t0 + mt * 128 + row, tb = ta + 8;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      q[2 * g] = make_float2(0.f, 0.f);
+      q[2 * g + 1] = make_float2(0.f, 0.f);
+      if (src && add) {
+        if (ta < lim) q[2 * g] = *reinterpret_cast<const float2*>(src + (size_t)ta * a.y_ld + 8 * g);
+        if (tb < lim) q[2 * g + 1] = *reinterpret_cast<const float2*>(src + (size_t)tb * a.y_ld + 8 * g);
+      }
+    }
+  };
+
+  float2 rq[8];
+  if (nblk > 0) prefetch(0, rq);
+  mbar_wait(bar, parity);
+  tc::fence_after();
+#pragma unroll 1
+  for (int k = 0; k < nblk; ++k) {
+    int mt, c0, row;
+    geom(k, mt, c0, row);
+    const int ta = t0 + mt * 128 + row, tb = ta + 8;
+    const bool oka = ta < lim, okb = tb < lim;
+    const uint32_t taddr = acc + ((uint32_t)(lane_base + 16 * (k & 1)) << 16) + 2 * mt * TN + c0;
+    uint32_t rm[16], rl[16];
+    tc::tmem_ld16x256_x4_issue(taddr, rm);
+    if (two) tc::tmem_ld16x256_x4_issue(taddr + TN, rl);
+    // under the TMEM read: the next block's operand, this block's bias (and previous output when accumulating)
+    float2 rn[8];
+    if (k + 1 < nblk) {
+      prefetch(k + 1, rn);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) rn[g] = make_float2(0.f, 0.f);
+    }
+    float2 bq[4], ya[4], yc[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bq[g] = __ldg(reinterpret_cast<const float2*>(bias + n0 + c0 + 8 * g + csub));
+    const bool accum = a.epi == 0 && a.accumulate;
+    if (accum) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        ya[g] = make_float2(0.f, 0.f);
+        yc[g] = make_float2(0.f, 0.f);
+        if (oka) ya[g] = *reinterpret_cast<const float2*>(yb + (size_t)ta * a.y_ld + n0 + c0 + 8 * g + csub);
+        if (okb) yc[g] = *reinterpret_cast<const float2*>(yb + (size_t)tb * a.y_ld + n0 + c0 + 8 * g + csub);
+      }
+    }
+    float v[16];
+    if (two) {
+      tc::tmem_ld_wait16x2(rm, rl);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(rl[i]), tc::kLoInv, __uint_as_float(rm[i]));
+    } else {
+      tc::tmem_ld_wait16(rm);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rm[i]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      v[4 * g] += bq[g].x; v[4 * g + 1] += bq[g].y; v[4 * g + 2] += bq[g].x; v[4 * g + 3] += bq[g].y;
+    }
+    if (a.epi == 0) {
+      // ---- linear: bias, residual, MRF accumulate, scale
+      float* ypa = yb + (size_t)ta * a.y_ld + n0 + c0 + csub;
+      float* ypb = yb + (size_t)tb * a.y_ld + n0 + c0 + csub;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float2 oa = make_float2(v[4 * g] + rq[2 * g].x, v[4 * g + 1] + rq[2 * g].y);
+        float2 ob = make_float2(v[4 * g + 2] + rq[2 * g + 1].x, v[4 * g + 3] + rq[2 * g + 1].y);
+        if (accum) {
+          oa.x = ya[g].x + oa.x; oa.y = ya[g].y + oa.y;
+          ob.x = yc[g].x + ob.x; ob.y = yc[g].y + ob.y;
+        }
+        if (a.scale != 1.f) { oa.x *= a.scale; oa.y *= a.scale; ob.x *= a.scale; ob.y *= a.scale; }
+        if (oka) *reinterpret_cast<float2*>(ypa + 8 * g) = oa;
+        if (okb) *reinterpret_cast<float2*>(ypb + 8 * g) = ob;
+      }
+    } else if (a.epi == 1) {
+      // ---- WaveNet gate (modules.py:185-210): columns [0,16) of the group are the tanh inputs of 16 channels,
+      // [16,32) their sigmoid partners -> 16 output channels at column (n0 + c0) / 2
+      float* ypa = yb + (size_t)ta * a.y_ld + ((n0 + c0) >> 1) + csub;
+      float* ypb = yb + (size_t)tb * a.y_ld + ((n0 + c0) >> 1) + csub;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const float2 oa = make_float2(tanhf(v[4 * g]) * sigmoidf_acc(v[4 * (g + 2)]),
+                                      tanhf(v[4 * g + 1]) * sigmoidf_acc(v[4 * (g + 2) + 1]));
+        const float2 ob = make_float2(tanhf(v[4 * g + 2]) * sigmoidf_acc(v[4 * (g + 2) + 2]),
+                                      tanhf(v[4 * g + 3]) * sigmoidf_acc(v[4 * (g + 2) + 3]));
+        if (oka) *reinterpret_cast<float2*>(ypa + 8 * g) = oa;
+        if (okb) *reinterpret_cast<float2*>(ypb + 8 * g) = ob;
+      }
+    } else {
+      // ---- WaveNet res/skip: columns < split update x in place (x += res), the rest go to the skip sum (= / +=)
+      bool add;
+      float* dst = const_cast<float*>(operand(c0, add));
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float2 oa = make_float2(rq[2 * g].x + v[4 * g], rq[2 * g].y + v[4 * g + 1]);
+        const float2 ob = make_float2(rq[2 * g + 1].x + v[4 * g + 2], rq[2 * g + 1].y + v[4 * g + 3]);
+        if (oka) *reinterpret_cast<float2*>(dst + (size_t)ta * a.y_ld + 8 * g) = oa;
+        if (okb) *reinterpret_cast<float2*>(dst + (size_t)tb * a.y_ld + 8 * g) = ob;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) rq[g] = rn[g];
   }
 }
 
@@ -265,11 +315,12 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
       }
     }
   } else if (warp == 1 || (NISS == 2 && warp == 6)) {
-    // ------------------------------------------------------------ MMA issuers (one thread each)
-    // The loop body is kept minimal on purpose: this single thread's instruction latency must stay below the
-    // tensor pipe's time per instruction.  Descriptors differ only in their 14-bit start-address field, so they
-    // are advanced by plain adds.
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuers (one elected thread per warp)
+    // The whole warp runs the loop converged and only the tcgen05 instructions are predicated on elect.sync: the
+    // descriptors then live in uniform registers and advance by plain adds (they differ only in their 14-bit
+    // start-address field).  [A divergent `if (lane == 0)` around the loop made ptxas wrap every MMA in an
+    // ELECT / R2UR / BRA.U.ANY replay sequence: ~60 dependent instructions per MMA pair, 35 % tensor-pipe activity.]
+    {
       const int mt_lo = (warp == 1 ? 0 : MT / NISS), mt_hi = mt_lo + MT / NISS;
       const uint32_t idesc1 = tc::make_idesc_f16(128, TN), idesc2 = tc::make_idesc_f16(128, 2 * TN);
       constexpr uint32_t LBO_A = ROWS * 16, LBO_B = 2 * TN * 16, SBO = 128;
@@ -293,16 +344,21 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
             tc::fence_after();
             const uint64_t b_slot = b_ring + (uint32_t)slot * SLOT16;
             // output step (t0 + mt*128 + i) reads staged row (mt*128 + i + tap*DIL): the halo tile starts at t0 - H
-            OVC_TC_ISSUE_MMAS(tmem_d)
+            if (tc::elect_one()) {
+              OVC_TC_ISSUE_MMAS(tmem_d)
+              tc::mma_commit(&b_empty[slot]);       // slot reusable once these MMAs have read it
+            }
+            __syncwarp();
             first = false;
-            tc::mma_commit(&b_empty[slot]);       // slot reusable once these MMAs have read it
             a_cur += dil;
             if (++slot == SLOTS) { slot = 0; bphase ^= 1; }
           }
         }
-        tc::mma_commit(&a_empty[buf]);
+        if (tc::elect_one()) tc::mma_commit(&a_empty[buf]);
+        __syncwarp();
       }
-      tc::mma_commit(acc_full);
+      if (tc::elect_one()) tc::mma_commit(acc_full);
+      __syncwarp();
     }
   } else if (warp >= 2 && warp <= 5) {
     // ------------------------------------------------------------ A producers, then epilogue
@@ -353,9 +409,7 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
       mbar_arrive(&a_full[buf]);
     }
     // epilogue: warp w may read TMEM lanes [32*(w%4), +32)
-    mbar_wait(acc_full, 0);
-    tc::fence_after();
-    tc_epilogue<TN, MT>(a, tmem_d, b, t0, n0, lim, warp, lane, 0, MT);
+    tc_epilogue<TN, MT>(a, tmem_d, b, t0, n0, lim, warp, lane, 0, MT, 0, TN, acc_full, 0);
   }
   tc::fence_before();
   __syncthreads();
@@ -499,8 +553,8 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
       }
     }
   } else if (warp == 1 || (NISS == 2 && warp == 2)) {
-    // ------------------------------------------------------------ MMA issuers (one thread each)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuers (one elected thread per warp, converged loop)
+    {
       const int mt_lo = (warp - 1) * (MT / NISS), mt_hi = mt_lo + MT / NISS;
       const uint32_t idesc1 = tc::make_idesc_f16(128, TN), idesc2 = tc::make_idesc_f16(128, 2 * TN);
       constexpr uint32_t LBO_A = ROWS * 16, LBO_B = 2 * TN * 16, SBO = 128;
@@ -530,17 +584,22 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
                 tc::fence_after();
               }
               const uint64_t b_slot = b_ring + (uint32_t)slot * SLOT16;
-              OVC_TC_ISSUE_MMAS(acc)
+              if (tc::elect_one()) {
+                OVC_TC_ISSUE_MMAS(acc)
+                if (!resident) tc::mma_commit(&b_empty[slot]);
+              }
+              __syncwarp();
               first = false;
-              if (!resident) tc::mma_commit(&b_empty[slot]);
               a_cur += dil;
               if (++slot == RING) { slot = 0; bphase ^= 1; }
             }
           }
-          tc::mma_commit(&a_empty[buf]);
+          if (tc::elect_one()) tc::mma_commit(&a_empty[buf]);
+          __syncwarp();
           if (++buf == NABUF) { buf = 0; aphase ^= 1; }
         }
-        tc::mma_commit(&acc_full[set]);
+        if (tc::elect_one()) tc::mma_commit(&acc_full[set]);
+        __syncwarp();
         ++n;
       }
     }
@@ -622,9 +681,8 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
     int n = 0;
     TCN_FOR_TILES
       const int set = n & 1;
-      mbar_wait(&acc_full[set], (n >> 1) & 1);
-      tc::fence_after();
-      tc_epilogue<TN, MT>(a, tmem_d + set * SET_COLS, b, t0, n0, lim, warp, lane, mt_lo, mt_hi, c_lo, c_hi);
+      tc_epilogue<TN, MT>(a, tmem_d + set * SET_COLS, b, t0, n0, lim, warp, lane, mt_lo, mt_hi, c_lo, c_hi, &acc_full[set],
+                          (n >> 1) & 1);
       tc::fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[set]);
