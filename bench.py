@@ -486,8 +486,8 @@ def main():
     for name, ms, fl, by, f in detail:
         if not f:
             continue
-        key = {"T128": "tcconv_wide_kernel (C >= 128)", "T64c": "tcconv_narrow_kernel<64> (C = 64)",
-               "T32c": "tcconv_narrow_kernel<32> (C = 32)"}.get(name[:4], "conv1d_f32 (CUDA cores)")
+        key = {"T128": "tcconv_wide_kernel<1> / tcconv_kernel<128> (C >= 128)", "T64c": "tcconv_kernel<64> (C = 64)",
+               "T32c": "tcconv_kernel<32> (C = 32)"}.get(name[:4], "conv1d_f32 (CUDA cores)")
         a = fam.setdefault(key, [0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
 
@@ -506,6 +506,18 @@ def main():
                 continue
         return None, None
 
+    def ncu_dram_pass():
+        """average DRAM bytes per ResBlock conv launch from the committed single-pass ncu run of THIS workload (batch 32 x 10 s,
+        f16x3: tools/gpu_ncu.sh -> tools/summarize_ncu.py dram); only valid for the default batch / length / precision"""
+        import glob
+        if (B, secs, args.precision) != (32, 10.0, "f16x3"):
+            return None, "no ncu DRAM pass for this batch / length / precision (committed one: batch 32 x 10 s, f16x3)"
+        paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_ncu_dram_b32_f16x3.json")))
+        if not paths:
+            return None, None
+        cap = json.load(open(paths[-1]))
+        return cap["dram_bytes_per_launch_avg"], f"{os.path.basename(paths[-1])}: {cap['what']} (average over the 72 launches)"
+
     if args.precision == "fp32":
         traffic, traffic_note = ncu_traffic("r0*_ncu_full_A_K11D1_ffma2.json")
         roofline = {
@@ -522,14 +534,14 @@ def main():
         # precision spends 3 tensor FLOPs per algorithmic FLOP, which shows up as pipe_occupancy, not as achieved work.
         passes = 3 if args.precision == "f16x3" else 1
         tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        traffic, traffic_note = ncu_traffic("r02_ncu_full_wide_*.json")
+        traffic, traffic_note = ncu_dram_pass()
         roofline = {
-            "kernel": "tcconv_wide_kernel + tcconv_narrow_kernel (generator ResBlock1 convs on tcgen05, 72 launches per call)",
+            "kernel": "tcconv_wide_kernel<1> (k >= 7 at C >= 128) + tcconv_kernel<128|64|32> (generator ResBlock1 convs on tcgen05, 72 launches per call)",
             "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach_tf / tc_peak,
             "frac_note": "algorithmic FLOPs / time / measured dense 16-bit tensor peak; the fp32-grade split precision needs "
                          "3 MMA passes, so 1/3 is the ceiling of this mode",
             "mma_passes": passes, "pipe_occupancy": ach_tf * passes / tc_peak,
-            "traffic": traffic, "traffic_note": traffic_note,
+            "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes_per_launch": prof["bytes"] / max(1, prof["launches"]),
             "peak_source": ("measured" if "bf16_tflops_sustained" in peaks else "fallback") + " dense bf16/fp16 sustained (MEASURED_PEAKS.json)",
             "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_prof_step,
             "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src,

@@ -177,9 +177,9 @@ OVC_API int ovc_tts_decode(ovc_ctx* ctx, const float* noise, uint64_t seed, floa
 OVC_API int ovc_set_precision(ovc_ctx* ctx, int mode);
 
 /* Tuning / diagnostics switches (never change results beyond fp32 reordering):
- *   OVC_OPT_WIDE_VARIANT  kernel of the 128-column tensor-core layers: 0 (default) the persistent kernel (one CTA per
- *                         SM, TMA-staged activations, overlapped epilogue); 1: one 256-step tile per CTA; 2: one
- *                         128-step tile per CTA, two CTAs per SM
+ *   OVC_OPT_WIDE_VARIANT  kernel of the 128-column tensor-core layers: 0 the persistent kernel (one CTA per SM,
+ *                         TMA-staged activations, overlapped epilogue); 1: one 256-step tile per CTA; 2: one 128-step
+ *                         tile per CTA, two CTAs per SM; 3 (default): 2 for k >= 7 at Cin >= 256, else 0
  *   OVC_OPT_TTS_SIMPLE    1: one-thread-per-element text-side kernels (the CPU-checked element functions) instead of
  *                         the warp-cooperative LayerNorm / fused attention
  *   OVC_OPT_ACT_TMA       1 (default): the persistent conv kernel receives its activation tiles by tensor-map TMA;
@@ -193,6 +193,11 @@ OVC_API int ovc_set_option(ovc_ctx* ctx, int key, int value);
 
 /* Number of kernels the last ovc_voice_conversion / ovc_convert_waveform call launched. */
 OVC_API int ovc_last_launch_count(const ovc_ctx* ctx);
+
+/* Number of ovc_voice_conversion / ovc_convert_waveform calls served by replaying a captured CUDA graph (OVC_OPT_GRAPH)
+ * since the context was created.  A (shapes, buffers, options) signature is captured the second time it is seen and
+ * replayed from the third call on; results are bit-identical to the directly launched sequence. */
+OVC_API int ovc_graph_replays(const ovc_ctx* ctx);
 
 /* Per-call timing hook for bench.py's roofline: when enabled, the dominant kernel family
  * (generator ResBlock convolutions) is bracketed with CUDA events on `stream`.  After the

@@ -19,7 +19,7 @@ EXPORTS = (
     "ovc_finalize_weights", "ovc_workspace_floats", "ovc_voice_conversion", "ovc_last_launch_count",
     "ovc_profile_enable", "ovc_profile_read", "ovc_profile_detail", "ovc_debug_enable", "ovc_debug_fetch",
     "ovc_spectrogram", "ovc_convert_waveform", "ovc_set_precision", "ovc_reference_encoder",
-    "ovc_tts_info", "ovc_tts_encode", "ovc_tts_decode", "ovc_set_option",
+    "ovc_tts_info", "ovc_tts_encode", "ovc_tts_decode", "ovc_set_option", "ovc_graph_replays",
 )
 
 
@@ -70,6 +70,8 @@ def load_library(path: Optional[str] = None):
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float,
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ovc_last_launch_count.argtypes = [C.c_void_p]
+    lib.ovc_graph_replays.argtypes = [C.c_void_p]
+    lib.ovc_graph_replays.restype = C.c_int
     lib.ovc_set_precision.argtypes = [C.c_void_p, C.c_int]
     lib.ovc_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.ovc_reference_encoder.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -195,7 +197,7 @@ class NativeConverter:
         self.precision = mode
 
     def set_option(self, key: str, value: int):
-        """Tuning switches of include/ovc.h: 'wide_variant' (0/1/2), 'tts_simple' (0/1), 'graph' (0/1), 'act_tma' (0/1)."""
+        """Tuning switches of include/ovc.h: 'wide_variant' (0/1/2/3), 'tts_simple' (0/1), 'graph' (0/1), 'act_tma' (0/1)."""
         k = {"wide_variant": 1, "tts_simple": 2, "graph": 3, "act_tma": 4}[key]
         _check(self.lib, self.lib.ovc_set_option(self.handle, k, int(value)), "ovc_set_option")
 
@@ -245,9 +247,12 @@ class NativeConverter:
         _check(self.lib, rc, "ovc_spectrogram")
         return spec, frames
 
-    def convert_waveform(self, wav, wav_lengths, g_src, g_tgt, noise=None, tau: float = 0.3, seed: int = 0, stream=None):
+    def convert_waveform(self, wav, wav_lengths, g_src, g_tgt, noise=None, tau: float = 0.3, seed: int = 0, stream=None,
+                         out=None, frames_out=None):
         """The device work of ToneColorConverter.convert for a batch: wav [B, Lmax] f32 cuda ->
-        (o_hat [B, hop * (Lmax // hop)], frames [B]).  Asynchronous on `stream`."""
+        (o_hat [B, hop * (Lmax // hop)], frames [B]).  Asynchronous on `stream`.  ``out`` / ``frames_out`` let the
+        caller supply the result buffers: with every buffer at a stable address, a repeated call is replayed from a
+        CUDA graph (include/ovc.h: OVC_OPT_GRAPH)."""
         import torch
         assert wav.is_cuda and wav.dtype == torch.float32 and wav.is_contiguous() and wav.dim() == 2
         assert wav_lengths.is_cuda and wav_lengths.dtype == torch.int64
@@ -258,8 +263,16 @@ class NativeConverter:
         if noise is not None:
             noise = noise.contiguous().float()
             assert tuple(noise.shape) == (B, self.hp.inter_channels, T)
-        o = torch.empty(B, self.hp.hop_length * T, device=wav.device, dtype=torch.float32)
-        frames = torch.empty(B, device=wav.device, dtype=torch.int64)
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == B * self.hp.hop_length * T
+            o = out.view(B, self.hp.hop_length * T)
+        else:
+            o = torch.empty(B, self.hp.hop_length * T, device=wav.device, dtype=torch.float32)
+        if frames_out is not None:
+            assert frames_out.is_cuda and frames_out.dtype == torch.int64 and frames_out.numel() == B
+            frames = frames_out
+        else:
+            frames = torch.empty(B, device=wav.device, dtype=torch.int64)
         st = stream if stream is not None else torch.cuda.current_stream(wav.device)
         rc = self.lib.ovc_convert_waveform(
             self.handle, C.c_void_p(wav.data_ptr()), C.c_void_p(wav_lengths.data_ptr()), B, L, C.c_void_p(gs.data_ptr()),
@@ -335,6 +348,11 @@ class NativeConverter:
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.ovc_last_launch_count(self.handle))
+
+    @property
+    def graph_replays(self) -> int:
+        """calls served from a captured CUDA graph so far (include/ovc.h: ovc_graph_replays)"""
+        return int(self.lib.ovc_graph_replays(self.handle))
 
     # ---- instrumentation -------------------------------------------------------------------
     def profile_enable(self, on: bool):

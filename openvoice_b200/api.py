@@ -68,6 +68,28 @@ def _write_audio(path: str, audio: np.ndarray, sr: int) -> None:
         wavfile.write(path, sr, audio.astype(np.float32))
 
 
+def watermark_device(audio, payload_bits, model, chunk: int = 16000, stride: int = 32000):
+    """On-device chunking of openvoice/api.py:162-184.  ``audio``: 1-D float32 tensor (any device), modified in place;
+    ``payload_bits``: flat 0/1 array, 32 per chunk.  Chunk n = samples [n * stride, n * stride + chunk); as in the
+    reference the walk stops at the first chunk that does not fit ("Audio too short").  All full chunks are gathered
+    by a strided view (no copy), encoded by ONE batched ``model.encode([m, chunk], [m, 32])`` call and scattered back."""
+    n_repeat = len(payload_bits) // 32
+    L = int(audio.shape[0])
+    m = 0
+    while m < n_repeat and m * stride + chunk <= L:
+        m += 1
+    if m < n_repeat:
+        print("Audio too short, fail to add watermark")
+    if m == 0:
+        return audio
+    with torch.no_grad():
+        view = torch.as_strided(audio, (m, chunk), (stride, 1))
+        bits = torch.as_tensor(np.asarray(payload_bits[: 32 * m], dtype=np.float32).reshape(m, 32), device=audio.device)
+        enc = model.encode(view.contiguous(), bits).detach().reshape(m, chunk).to(audio.dtype)
+        view.copy_(enc)
+    return audio
+
+
 class NativeSynthesizer:
     """Stands where ``SynthesizerTrn`` stands in the reference (``converter.model``) for the
     ``n_speakers == 0`` converter (openvoice/models.py:399-465): ``voice_conversion``,
@@ -510,10 +532,18 @@ class ToneColorConverter(OpenVoiceBaseClass):
             if len(w) < Lmax:
                 stage[b, len(w):] = 0.0
             lens[b] = len(w)
-        wav = stage.to(dev, non_blocking=True)
+        # device-side buffers are cached per slot too: with every address stable, a repeated (batch, length) call is
+        # replayed from a CUDA graph by the native library (include/ovc.h: OVC_OPT_GRAPH)
+        wav = self._dev(f"wav{slot}", B * Lmax, torch.float32).view(B, Lmax)
+        wav.copy_(stage, non_blocking=True)
         lens_pin = self._pinned_i64(f"len{slot}", B)
         lens_pin.copy_(torch.from_numpy(lens))
-        wlen = lens_pin.to(dev, non_blocking=True)
+        wlen = self._dev(f"len{slot}", B, torch.int64)
+        wlen.copy_(lens_pin, non_blocking=True)
+        src_d = self._dev(f"src{slot}", src.numel(), torch.float32).view(B, -1)
+        src_d.copy_(src.reshape(B, -1), non_blocking=True)
+        tgt_d = self._dev(f"tgt{slot}", tgt.numel(), torch.float32).view(B, -1)
+        tgt_d.copy_(tgt.reshape(B, -1), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         self._h2d_done[slot] = ev
@@ -525,7 +555,9 @@ class ToneColorConverter(OpenVoiceBaseClass):
                 nz[b, :, : q.shape[1]] = q.to(dev)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         # spectrogram + voice_conversion, every item at its own exact length (api.py:148-154)
-        o, _ = self.model.native.convert_waveform(wav, wlen, src, tgt, noise=nz, tau=float(tau), seed=seed)
+        o, _ = self.model.native.convert_waveform(wav, wlen, src_d, tgt_d, noise=nz, tau=float(tau), seed=seed,
+                                                  out=self._dev(f"out{slot}", B * (Lmax // hop) * hop, torch.float32),
+                                                  frames_out=self._dev(f"fr{slot}", B, torch.int64))
         return o.view(B, -1), frames
 
     def _convert_chunk(self, waves, src, tgt, tau, noise):
@@ -549,6 +581,15 @@ class ToneColorConverter(OpenVoiceBaseClass):
         o, frames = self._enqueue_chunk(waves, self._stack_se(src_se, n), self._stack_se(tgt_se, n), tau, None, slot)
         hop = self.hps.data.hop_length
         return o, [f * hop for f in frames]
+
+    def _dev(self, name, numel, dtype):
+        """Grow-only device buffers (per upload slot): the result of slot s is overwritten by the next call on slot s."""
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        buf = cache.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty(int(numel * 1.25) + 64, dtype=dtype, device=self.device)
+            cache[name] = buf
+        return buf[:numel]
 
     def _pinned_i64(self, name, numel):
         cache = self.__dict__.setdefault("_pin_cache", {})
@@ -579,18 +620,14 @@ class ToneColorConverter(OpenVoiceBaseClass):
 
     def add_watermark(self, audio, message):
         """Embed ``message`` with the wavmark model, 32 bits per 16000-sample chunk, chunks 32000 samples apart
-        (behaviour of openvoice/api.py:162-184, incl. the "Audio too short" early stop).  No model -> no-op."""
+        (behaviour of openvoice/api.py:162-184, incl. the "Audio too short" early stop).  No model -> no-op.
+        The chunks are cut, encoded and written back ON THE DEVICE as one batch (``watermark_device``): one upload and
+        one download per utterance instead of two host round trips per chunk."""
         if self.watermark_model is None:
             return audio
-        payload = utils.string_to_bits(message).reshape(-1)
-        for n, sl, full in self._wm_chunks(audio, len(payload) // 32):
-            if not full:
-                print("Audio too short, fail to add watermark")
-                break
-            with torch.no_grad():
-                sig = torch.as_tensor(audio[sl], dtype=torch.float32, device=self.device)[None]
-                bits = torch.as_tensor(payload[32 * n: 32 * (n + 1)], dtype=torch.float32, device=self.device)[None]
-                audio[sl] = self.watermark_model.encode(sig, bits).detach().cpu().squeeze()
+        dev_audio = torch.as_tensor(audio, dtype=torch.float32).to(self.device)
+        watermark_device(dev_audio, utils.string_to_bits(message).reshape(-1), self.watermark_model)
+        audio[...] = dev_audio.cpu().numpy()
         return audio
 
     def detect_watermark(self, audio, n_repeat):

@@ -43,6 +43,9 @@ enum EpiKind : int {
 
 enum : int { F_ACCUM = 1, F_FIRST = 2 };
 
+// per-call scalars that live in device memory so that a captured launch sequence (CUDA graph) can be replayed with new values
+struct CallParams { unsigned long long seed; float tau; float pad; };
+
 struct ConvArgs {
   // input activations, [B][cin][x_pitch] (time fastest)
   const float* x; long long x_bs; int x_pitch; int cin;
@@ -63,6 +66,7 @@ struct ConvArgs {
   int flags;        // F_ACCUM, F_FIRST
   int split;        // RESSKIP: rows < split update x, rows >= split go to skip[row-split]
   unsigned long long seed;   // PROJ without explicit noise
+  const CallParams* callp;   // PROJ: when set, seed and tau are read from here instead (graph replay)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -539,6 +543,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) conv1d_f32(const Co
     const int ch0 = row0 / 2;
     float* yb = a.y + (size_t)b * a.y_bs;
     const float* nb = a.r ? a.r + (size_t)b * a.r_bs : nullptr;
+    const unsigned long long seed = a.callp ? a.callp->seed : a.seed;
+    const float tau = a.callp ? a.callp->tau : a.tau;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int t = t0 + tb + 32 * c;
@@ -550,8 +556,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS) conv1d_f32(const Co
             const float m = acc[c][r][j] + bias[r];
             const float logs = acc[c][r + 4][j] + bias[r + 4];
             const float nz = nb ? nb[(size_t)(ch0 + r) * a.r_pitch + t + j]
-                                : philox_normal(a.seed, (uint32_t)b, (uint32_t)(ch0 + r), (uint32_t)(t + j));
-            yb[(size_t)(ch0 + r) * a.y_pitch + t + j] = m + nz * a.tau * expf(logs);
+                                : philox_normal(seed, (uint32_t)b, (uint32_t)(ch0 + r), (uint32_t)(t + j));
+            yb[(size_t)(ch0 + r) * a.y_pitch + t + j] = m + nz * tau * expf(logs);
           }
         }
       }

@@ -188,7 +188,7 @@ struct ovc_ctx {
   float* d_tcw = nullptr;      // tensor-core weight arena (hi/lo split)
   std::vector<float> h_tcw;
   int precision = 0;           // 0: fp32 FFMA everywhere; 1: 3xFP16 split-precision tcgen05 convs; 2: single-pass fp16
-  int wide_variant = 0;        // tiling of the 128-column tensor-core kernel (see launch_tc)
+  int wide_variant = 3;        // kernel of the 128-column tensor-core layers (see launch_tc); 3 = chosen per layer
   bool act_tma = true;         // OVC_OPT_ACT_TMA
   bool tts_simple = false;     // OVC_OPT_TTS_SIMPLE
   bool use_graph = true;       // OVC_OPT_GRAPH
@@ -237,11 +237,28 @@ struct ovc_ctx {
   std::map<std::string, DebugBuf> taps;
 
   int launches = 0;
+
+  // CUDA-graph replay of a repeated call (OVC_OPT_GRAPH): the launch sequence of a (entry point, shapes, buffers,
+  // options) signature is captured on an internal stream the second time it is seen and replayed from then on; the
+  // per-call scalars (noise seed, tau) reach the kernels through d_callp
+  struct GraphEntry {
+    std::vector<uintptr_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    int seen = 0;
+    uint64_t stamp = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
+  ovc::CallParams* d_callp = nullptr;
+  int graph_replays = 0;       // diagnostics: calls served by a replay since creation
 };
 
 namespace ovc {
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+static void drop_graphs(ovc_ctx* c);
 
 static const HostTensor* find(const ovc_ctx* c, const std::string& k) {
   auto it = c->sd.find(k);
@@ -441,6 +458,7 @@ static int finalize(ovc_ctx* c) {
   const ovc_hparams& hp = c->hp;
   const int H = 192, S = hp.spec_channels, G = hp.gin_channels;
   std::string miss;
+  drop_graphs(c);               // captured launches point at the old weight arenas
   c->h_w.clear();
   c->h_tcw.clear();
 #define NEED(ptr, key)                                                                     \
@@ -875,7 +893,10 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   a.passes = r.c->precision == 2 ? 1 : 3;
   if (T.TN == 0) return fail(OVC_ERR_INVALID, "conv %d -> %d (k %d, dilation %d) does not fit the tensor-core kernels", T.Cin, T.Ntot, T.K, T.DIL);
   TRY(prof_begin(r));
-  const int wv = r.c->wide_variant;
+  // 3 (default): the generator's first stage (k >= 7 at C = 256: few, long tiles) on the two-CTAs-per-SM kernel, whose
+  // second CTA fills the tensor pipe while the first waits on a barrier; everything else on the persistent kernel
+  int wv = r.c->wide_variant;
+  if (wv == 3) wv = (T.K >= 7 && T.Cin >= 256) ? 2 : 0;
   if (T.TN == 128 && wv != 0) {
     // A/B alternatives of the 128-column layers: 1 = 256-step tiles, one CTA per SM; 2 = 128-step tiles, two CTAs per SM
     const int MT = wv == 1 ? 2 : 1;
@@ -1018,9 +1039,88 @@ static int run_flow(Run& r, const WsLayout& W, float* ws, bool reverse, const fl
   return OVC_OK;
 }
 
+static void drop_graphs(ovc_ctx* c) {
+  for (auto& g : c->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();
+}
+
+__global__ void set_call_params_kernel(CallParams* p, unsigned long long seed, float tau) {
+  p->seed = seed;
+  p->tau = tau;
+}
+
+// Run `body(stream)` -- a pure launch sequence -- directly, or replay it from a CUDA graph when the same signature `key`
+// has been seen before (captured on the second sighting: a one-off call never pays for an instantiation).  Capture
+// happens on an internal stream (the caller's may be the legacy default stream, which cannot be captured); the graph is
+// launched into the caller's stream.
+template <class Body>
+static int run_graphed(ovc_ctx* c, const std::vector<uintptr_t>& key, cudaStream_t st, Body body) {
+  if (!c->use_graph || c->prof || c->debug) return body(st);
+  ovc_ctx::GraphEntry* e = nullptr;
+  for (auto& g : c->graphs)
+    if (g.key == key) { e = &g; break; }
+  if (!e) {
+    if (c->graphs.size() >= 16) {   // evict the least recently used signature
+      size_t lru = 0;
+      for (size_t i = 1; i < c->graphs.size(); ++i)
+        if (c->graphs[i].stamp < c->graphs[lru].stamp) lru = i;
+      if (c->graphs[lru].exec) cudaGraphExecDestroy(c->graphs[lru].exec);
+      c->graphs.erase(c->graphs.begin() + lru);
+    }
+    c->graphs.emplace_back();
+    e = &c->graphs.back();
+    e->key = key;
+  }
+  e->stamp = ++c->graph_clock;
+  e->seen++;
+  if (e->exec) {
+    CK(cudaGraphLaunch(e->exec, st));
+    c->launches = e->launches;
+    c->graph_replays++;
+    return OVC_OK;
+  }
+  if (e->seen < 2) return body(st);
+  if (!c->cap_stream) CK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+  CK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = body(c->cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+  if (rc != OVC_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    e->seen = -1000000;           // never try this signature again
+    if (rc != OVC_OK) return rc;
+    return body(st);
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    e->exec = nullptr;
+    e->seen = -1000000;
+    return body(st);
+  }
+  e->launches = c->launches;
+  CK(cudaGraphLaunch(e->exec, st));
+  c->graph_replays++;
+  return OVC_OK;
+}
+
+static int set_call_params(ovc_ctx* c, uint64_t seed, float tau, cudaStream_t st) {
+  if (!c->d_callp) CK(cudaMalloc(&c->d_callp, sizeof(CallParams)));
+  set_call_params_kernel<<<1, 1, 0, st>>>(c->d_callp, seed, tau);
+  CK(cudaGetLastError());
+  return OVC_OK;
+}
+static uintptr_t option_bits(const ovc_ctx* c) {
+  return (uintptr_t)c->precision | ((uintptr_t)c->wide_variant << 4) | ((uintptr_t)c->act_tma << 8);
+}
+
 static int ensure_ws(ovc_ctx* c, const WsLayout& W, int B, int Tmax, cudaStream_t st) {
   if (W.total <= c->ws_floats) return OVC_OK;
   CK(cudaStreamSynchronize(st));
+  drop_graphs(c);               // captured launches point into the old workspace
   if (c->d_ws) CK(cudaFree(c->d_ws));
   c->d_ws = nullptr;
   c->ws_floats = 0;
@@ -1225,6 +1325,7 @@ static int run_vc(ovc_ctx* c, const float* spec, int spec_pitch, const long long
     p.r = noise; p.r_bs = 192LL * Tmax; p.r_pitch = Tmax;
     p.lens_in = lens; p.lens_out = lens; p.mul_in = 1; p.mul_out = 1;
     p.slope = 1.f; p.tau = tau; p.seed = seed;
+    p.callp = c->d_callp;       // set_call_params_kernel wrote (seed, tau) there earlier on this stream
     TRY(launch(r, c->enc_proj, p, Tmax));
   }
   auto copy_latent = [&](float* dst) -> int { return copy_latent_out(r, W, ws, dst); };
@@ -1288,6 +1389,9 @@ void ovc_destroy(ovc_ctx* c) {
   if (c->d_re) cudaFree(c->d_re);
   if (c->d_tw) cudaFree(c->d_tw);
   if (c->d_win) cudaFree(c->d_win);
+  drop_graphs(c);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  if (c->d_callp) cudaFree(c->d_callp);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& kv : c->taps)
     if (kv.second.d) cudaFree(kv.second.d);
@@ -1329,8 +1433,15 @@ int ovc_voice_conversion(ovc_ctx* c, const float* spec, const int64_t* lengths, 
   if (B > 65535) return fail(OVC_ERR_INVALID, "B %d exceeds the grid limit", B);
   ON_DEVICE(c);
   c->ev_used = c->prof ? c->ev_used : 0;
-  return run_vc(c, spec, Tmax, (const long long*)lengths, g_src, g_tgt, noise, seed, tau, B, Tmax, ragged, o_hat, z, z_p, z_hat,
-                (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(ensure_ws(c, ws_layout(c, B, Tmax), B, Tmax, st));
+  TRY(set_call_params(c, seed, tau, st));
+  const std::vector<uintptr_t> key = {1, (uintptr_t)spec, (uintptr_t)lengths, (uintptr_t)g_src, (uintptr_t)g_tgt, (uintptr_t)noise,
+                                      (uintptr_t)o_hat, (uintptr_t)z, (uintptr_t)z_p, (uintptr_t)z_hat, (uintptr_t)B, (uintptr_t)Tmax,
+                                      (uintptr_t)ragged, option_bits(c)};
+  return run_graphed(c, key, st, [&](cudaStream_t s) {
+    return run_vc(c, spec, Tmax, (const long long*)lengths, g_src, g_tgt, noise, seed, tau, B, Tmax, ragged, o_hat, z, z_p, z_hat, s);
+  });
 }
 
 static int launch_stft(ovc_ctx* c, const float* wav, const int64_t* wav_lengths, int B, int Lmax, int Tmax, float* spec,
@@ -1368,13 +1479,18 @@ int ovc_convert_waveform(ovc_ctx* c, const float* wav, const int64_t* wav_length
   cudaStream_t st = (cudaStream_t)stream;
   const WsLayout W = ws_layout(c, B, Tmax);
   TRY(ensure_ws(c, W, B, Tmax, st));
-  float* spec = c->d_ws + W.spec;
-  long long* fr = reinterpret_cast<long long*>(c->d_ws + W.frames);
-  TRY(launch_stft(c, wav, wav_lengths, B, Lmax, Tmax, spec, W.P, fr, st));
-  if (frames) CK(cudaMemcpyAsync(frames, fr, (size_t)B * sizeof(long long), cudaMemcpyDeviceToDevice, st));
-  const int rc = run_vc(c, spec, W.P, fr, g_src, g_tgt, noise, seed, tau, B, Tmax, 1, o_hat, nullptr, nullptr, nullptr, st);
-  c->launches += 1;
-  return rc;
+  TRY(set_call_params(c, seed, tau, st));
+  const std::vector<uintptr_t> key = {2, (uintptr_t)wav, (uintptr_t)wav_lengths, (uintptr_t)g_src, (uintptr_t)g_tgt, (uintptr_t)noise,
+                                      (uintptr_t)o_hat, (uintptr_t)frames, (uintptr_t)B, (uintptr_t)Lmax, option_bits(c)};
+  return run_graphed(c, key, st, [&](cudaStream_t s) {
+    float* spec = c->d_ws + W.spec;
+    long long* fr = reinterpret_cast<long long*>(c->d_ws + W.frames);
+    TRY(launch_stft(c, wav, wav_lengths, B, Lmax, Tmax, spec, W.P, fr, s));
+    if (frames) CK(cudaMemcpyAsync(frames, fr, (size_t)B * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    const int rc = run_vc(c, spec, W.P, fr, g_src, g_tgt, noise, seed, tau, B, Tmax, 1, o_hat, nullptr, nullptr, nullptr, s);
+    c->launches += 1;
+    return rc;
+  });
 }
 
 int ovc_reference_encoder(ovc_ctx* c, const float* spec, int N, int T, float* out, void* stream) {
@@ -1482,7 +1598,7 @@ int ovc_set_option(ovc_ctx* c, int key, int value) {
   if (!c) return fail(OVC_ERR_INVALID, "null context");
   switch (key) {
     case OVC_OPT_WIDE_VARIANT:
-      if (value < 0 || value > 2) return fail(OVC_ERR_INVALID, "wide variant must be 0, 1 or 2");
+      if (value < 0 || value > 3) return fail(OVC_ERR_INVALID, "wide variant must be 0, 1, 2 or 3");
       c->wide_variant = value;
       return OVC_OK;
     case OVC_OPT_TTS_SIMPLE: c->tts_simple = value != 0; return OVC_OK;
@@ -1493,6 +1609,8 @@ int ovc_set_option(ovc_ctx* c, int key, int value) {
 }
 
 int ovc_last_launch_count(const ovc_ctx* c) { return c ? c->launches : 0; }
+
+int ovc_graph_replays(const ovc_ctx* c) { return c ? c->graph_replays : 0; }
 
 int ovc_profile_enable(ovc_ctx* c, int enable) {
   if (!c) return fail(OVC_ERR_INVALID, "null context");

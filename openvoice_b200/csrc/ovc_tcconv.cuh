@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
   const int lim = (a.lens ? (int)min((long long)a.tmax, a.lens[b]) : a.tmax) * a.mul;
   if (t0 >= lim) return;   // the tile lies past the utterance
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code may use uniform registers
   const int H = (a.K - 1) / 2 * a.DIL;
   const int nq = a.Cin / Cfg::KCH;            // A chunks
   const int n_slots = (a.Cin / 16) * a.K;
@@ -481,7 +482,8 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
   unsigned char* raw = bring + RING * Cfg::SLOT_BYTES;
   raw += (1024u - (smem_u32(raw) & 1023u)) & 1023u;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code may use uniform registers
   const int n0 = blockIdx.y * TN;
   const int H = (a.K - 1) / 2 * a.DIL;
   const int rows8 = tcn_rows(MT, H);

@@ -158,6 +158,11 @@ def convert_sharded_async(converter, audios: Sequence[np.ndarray], src_se, tgt_s
     state = converter.__dict__.setdefault("_shard_state", {"n": 0})
     k = state["n"] % 2
     state["n"] += 1
+    # the converter's device-side result buffer of slot k is reused by this call: the gather / download of the job that
+    # used it last (two calls ago) must have read it first
+    last = state.get(f"done{k}")
+    if last is not None and converter.device != "cpu" and torch.cuda.is_available():
+        torch.cuda.current_stream(converter.device).wait_event(last)
     if mine:
         o, _ = converter.convert_batch_device([audios[i] for i in mine], pick(src_se),
                                               [tgt_se[i] for i in mine] if isinstance(tgt_se, (list, tuple)) else tgt_se,
@@ -174,6 +179,7 @@ def convert_sharded_async(converter, audios: Sequence[np.ndarray], src_se, tgt_s
         if dev.type == "cuda":
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(dev))
+            state[f"done{k}"] = done
         return ShardedJob(done, table, host.numpy(), rank, dst, len(audios), copy)
     # fixed-shape block per rank (pad rows / columns), gathered on a side stream
     cuda = dev.type == "cuda"
@@ -207,6 +213,7 @@ def convert_sharded_async(converter, audios: Sequence[np.ndarray], src_se, tgt_s
         if cuda:
             done = torch.cuda.Event()
             done.record(side)
+            state[f"done{k}"] = done
     return ShardedJob(done, table, host.numpy() if host is not None else None, rank, dst, len(audios), copy)
 
 

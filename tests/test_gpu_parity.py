@@ -108,6 +108,41 @@ def test_batch_items_are_independent(native):
         assert torch.equal(latb[2][0], lat[2][b, :, :L])
 
 
+def test_graph_replay_is_bit_identical(native):
+    """OVC_OPT_GRAPH: a repeated (shapes, buffers) call is captured on its second sighting and replayed afterwards.
+    Replays must equal the directly launched sequence bit for bit, follow a new Philox seed, and stop when the
+    option is switched off."""
+    nat = native.native
+    B, L = 2, 22050
+    wav = (torch.rand(B, L, generator=torch.Generator().manual_seed(3)) - 0.5).cuda()
+    wlen = torch.tensor([L, L - 3000], dtype=torch.int64, device="cuda")
+    g1 = 0.1 * torch.randn(B, 256, generator=torch.Generator().manual_seed(4)).cuda()
+    g2 = 0.1 * torch.randn(B, 256, generator=torch.Generator().manual_seed(5)).cuda()
+    out = torch.empty(B, (L // 256) * 256, device="cuda")
+
+    def call(seed):
+        o, _ = nat.convert_waveform(wav, wlen, g1, g2, tau=0.3, seed=seed, out=out)
+        torch.cuda.synchronize()
+        return o.clone()
+
+    nat.set_option("graph", 0)
+    ref7, ref9 = call(7), call(9)
+    assert not torch.equal(ref7, ref9)
+    nat.set_option("graph", 1)
+    before = nat.graph_replays
+    a = call(7)                      # first sighting: direct
+    b = call(7)                      # second: captured, then launched as a graph
+    c = call(9)                      # replay with another seed
+    d = call(7)
+    assert nat.graph_replays - before >= 2, "the repeated call was not served from a graph"
+    assert torch.equal(a, ref7) and torch.equal(b, ref7) and torch.equal(d, ref7)
+    assert torch.equal(c, ref9)
+    launches = nat.last_launch_count
+    nat.set_option("graph", 0)
+    e = call(9)
+    assert torch.equal(e, ref9) and nat.last_launch_count == launches
+
+
 def test_flow_roundtrip_property_full_size(native):
     """Size-independent property at the BASELINE size (10 s clips, T=861): with g_src == g_tgt the
     reverse flow undoes the forward flow, so z_hat == z up to rounding."""
@@ -327,6 +362,48 @@ def test_time_tiled_long_clip_equals_whole_clip(tmp_path, synthetic_sd):
         assert rel_err(tiled, whole) <= 2e-6, precision
         short = conv.convert_long(wav[: 256 * 90], src, tgt, tau=0.0, window_frames=2048)     # single window
         assert np.array_equal(short, conv.convert(wav[: 256 * 90], src, tgt, tau=0.0))
+
+
+def test_streaming_equals_whole_clip(tmp_path, synthetic_sd):
+    """Row f4, stateful streaming: audio pushed in irregular chunks through StreamingConverter (spectrogram frames, noise
+    and audio tail carried between calls; window + 128-frame halo per call) gives the samples of convert on the whole
+    clip, emits them incrementally, and keeps a bounded state."""
+    from openvoice_b200.api import ToneColorConverter
+    from openvoice_b200.streaming import StreamingConverter
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps(O.DEFAULT_HPARAMS))
+    rng = np.random.default_rng(21)
+    L = 22050 * 9 + 77
+    wav = (0.5 * (2 * rng.random(L, dtype=np.float32) - 1)).astype(np.float32)
+    T = L // 256
+    gen = torch.Generator().manual_seed(9)
+    src = 0.1 * torch.randn(1, 256, 1, generator=gen)
+    tgt = 0.1 * torch.randn(1, 256, 1, generator=gen)
+    noise = torch.randn(192, T, generator=gen)
+    conv = ToneColorConverter(str(cfg), device="cuda:0", enable_watermark=False)
+    conv.model.load_state_dict(synthetic_sd)
+    whole = conv.convert(wav, src, tgt, tau=0.3, noise=noise[None])
+    for W, sizes in ((200, [100, 7000, 33, 66150, 12000, 256, 90001]), (64, [4096] * 60)):
+        sc = StreamingConverter(conv, src, tgt, tau=0.3, window_frames=W, noise_fn=lambda a, b: noise[:, a:b])
+        outs, pos, i, first_out_at, max_frames, max_samples = [], 0, 0, None, 0, 0
+        while pos < L:
+            n = min(sizes[i % len(sizes)], L - pos)
+            got = sc.push(wav[pos: pos + n])
+            pos += n
+            i += 1
+            if len(got) and first_out_at is None:
+                first_out_at = pos
+            outs.append(got)
+            max_frames, max_samples = max(max_frames, sc.state_frames), max(max_samples, sc.state_samples)
+        outs.append(sc.flush())
+        stream = np.concatenate(outs)
+        assert stream.shape == whole.shape == (256 * T,)
+        assert rel_err(stream, whole) <= 2e-6, W
+        # output starts once window + halo (+ the STFT support) has arrived, long before the end of the clip
+        assert first_out_at is not None and first_out_at <= 256 * (W + 128 + 4) + max(sizes)
+        # state: at most the two halos, one window and the frames of the largest chunk; audio tail of a few frames
+        assert max_frames <= W + 2 * 128 + max(sizes) // 256 + 8, max_frames
+        assert max_samples <= max(sizes) + 2048, max_samples
 
 
 def test_api_convert_matches_reference_golden(tmp_path, synthetic_sd):

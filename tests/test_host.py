@@ -255,3 +255,53 @@ def test_base_speaker_host_helpers():
     assert a.dtype == np.float32 and len(a) == 10 + 4 + 2 * gap
     assert a[:10].tolist() == [1.0] * 10 and a[10:10 + gap].tolist() == [0.0] * gap and a[10 + gap:14 + gap].tolist() == [2.0] * 4
     assert BaseSpeakerTTS.language_marks == {"english": "EN", "chinese": "ZH"}
+
+
+def test_on_device_watermark_chunking_matches_the_reference_loop(capsys):
+    """Row f4: watermark_device (strided chunk view, ONE batched encode, scatter) against the per-chunk loop of
+    openvoice/api.py:162-184 restated here, with a stand-in for the third-party wavmark model; incl. the
+    "Audio too short" early stop."""
+    import numpy as np
+    import torch
+    from openvoice_b200 import utils
+    from openvoice_b200.api import watermark_device
+
+    class FakeWM:
+        calls = []
+
+        def encode(self, sig, bits):                # [m, 16000], [m, 32] -> [m, 16000]
+            FakeWM.calls.append(tuple(sig.shape))
+            w = (bits * torch.arange(1, 33, dtype=torch.float32)).sum(1, keepdim=True) * 1e-4
+            return sig * (1.0 + w) + 1e-3 * torch.sin(torch.arange(sig.shape[1], dtype=torch.float32))[None] * w
+
+    def reference_loop(audio, message, model):
+        bits = utils.string_to_bits(message).reshape(-1)
+        K, coeff = 16000, 2
+        for n in range(len(bits) // 32):
+            trunck = audio[(coeff * n) * K: (coeff * n + 1) * K]
+            if len(trunck) != K:
+                print("Audio too short, fail to add watermark")
+                break
+            sig = torch.FloatTensor(trunck)[None]
+            msg = torch.FloatTensor(bits[n * 32: (n + 1) * 32])[None]
+            audio[(coeff * n) * K: (coeff * n + 1) * K] = model.encode(sig, msg).squeeze().numpy()
+        return audio
+
+    rng = np.random.default_rng(0)
+    message = "@MyShell"                             # 8 chars -> 64 bits -> 2 chunks
+    n_chunks = len(utils.string_to_bits(message).reshape(-1)) // 32
+    for L in (32000 * n_chunks + 5000, 32000 * (n_chunks - 1) + 16000, 32000 * (n_chunks - 1) + 15999, 15000):
+        a = rng.standard_normal(L).astype(np.float32)
+        want = reference_loop(a.copy(), message, FakeWM())
+        FakeWM.calls.clear()
+        t = torch.from_numpy(a.copy())
+        watermark_device(t, utils.string_to_bits(message).reshape(-1), FakeWM())
+        assert np.allclose(t.numpy(), want, rtol=1e-6, atol=1e-6), L    # batched vs per-chunk: same math, last-bit differences
+        assert len(FakeWM.calls) <= 1               # one batched encode for all chunks of the utterance
+        short = "too short" in capsys.readouterr().out
+        assert short == (L < 32000 * (n_chunks - 1) + 16000)
+
+
+def test_streaming_module_imports_without_gpu():
+    import openvoice_b200.streaming as S
+    assert hasattr(S, "StreamingConverter")

@@ -20,15 +20,21 @@ KEYS = [
     "dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
 ]
 
 
-def full(path, out):
+def full(path, out, what=None):
     rows = list(csv.reader(open(path)))
     hdr, units = rows[0], rows[1]
     res = []
     for r in rows[2:]:
         d = {"kernel": r[hdr.index("Kernel Name")]}
+        if what:
+            d["what"] = what
         for k in KEYS:
             if k in hdr:
                 d[k] = f"{r[hdr.index(k)]} {units[hdr.index(k)]}".strip()
@@ -70,5 +76,37 @@ def launches(path, out):
         print(f"{k['ms']:9.3f} ms {100 * k['share']:5.1f}% n={k['launches']:4d} {k['kernel']}")
 
 
+def dram(path, out, batch="32"):
+    """single-pass ncu of one call's tensor-core conv launches (tools/gpu_ncu.sh): DRAM bytes per launch of the generator's
+    ResBlock convs, in launch order (see tools/ncu_target.py for the order)."""
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        i = int(row["ID"])
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"]
+        v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(unit, 1.0)
+        per.setdefault(i, {"kernel": row["Kernel Name"].split("(")[0]})[row["Metric Name"]] = v
+    ids = sorted(per)
+    assert len(ids) == 172, f"expected the 172 tensor-core conv launches of one call, got {len(ids)}"
+    stages = {"stage0_C256": range(97, 115), "stage1_C128": range(116, 134), "stage2_C64": range(135, 153), "stage3_C32": range(154, 172)}
+    res = {"what": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none (single pass, no "
+                   f"replay), one convert call at batch {batch} x 10 s, f16x3; the 72 generator ResBlock conv launches", "stages": {}}
+    tot_b, tot_ms = 0.0, 0.0
+    for name, rng in stages.items():
+        b = sum(per[ids[k]]["dram__bytes_read.sum"] + per[ids[k]]["dram__bytes_write.sum"] for k in rng)
+        ms = sum(per[ids[k]]["gpu__time_duration.sum"] for k in rng)
+        kern = sorted({per[ids[k]]["kernel"] for k in rng})
+        res["stages"][name] = {"launches": len(rng), "dram_bytes": b, "ms_under_ncu": ms, "kernels": kern}
+        tot_b += b
+        tot_ms += ms
+    res["resblock_launches"] = 72
+    res["dram_bytes_per_launch_avg"] = tot_b / 72
+    res["dram_bytes_total"] = tot_b
+    res["ms_under_ncu_total"] = tot_ms
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "launches": launches}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"full": full, "launches": launches, "dram": dram}[sys.argv[1]](*sys.argv[2:])
