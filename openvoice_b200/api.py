@@ -68,6 +68,29 @@ def _write_audio(path: str, audio: np.ndarray, sr: int) -> None:
         wavfile.write(path, sr, audio.astype(np.float32))
 
 
+_POOL = None
+
+
+def _pool():
+    """Host-side staging threads: copying the utterances into / out of the pinned buffers is plain memcpy work (numpy
+    releases the GIL for it) that sits inside every end-to-end call."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        try:
+            n = len(os.sched_getaffinity(0))
+        except Exception:
+            n = os.cpu_count() or 1
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(8, n)), thread_name_prefix="ovc-stage")
+    return _POOL
+
+
+def _parallel(fn, n, min_items=4):
+    if n < min_items:
+        return [fn(i) for i in range(n)]
+    return list(_pool().map(fn, range(n)))
+
+
 def watermark_device(audio, payload_bits, model, chunk: int = 16000, stride: int = 32000):
     """On-device chunking of openvoice/api.py:162-184.  ``audio``: 1-D float32 tensor (any device), modified in place;
     ``payload_bits``: flat 0/1 array, 32 per chunk.  Chunk n = samples [n * stride, n * stride + chunk); as in the
@@ -526,12 +549,15 @@ class ToneColorConverter(OpenVoiceBaseClass):
         if ev is not None:
             ev.synchronize()
         stage = self._pinned(f"in{slot}", B * Lmax).view(B, Lmax)
-        lens = np.empty(B, dtype=np.int64)
-        for b, w in enumerate(waves):
-            stage[b, : len(w)] = torch.from_numpy(w)
+        stage_np = stage.numpy()
+        lens = np.array([len(w) for w in waves], dtype=np.int64)
+
+        def put(b):
+            w = waves[b]
+            stage_np[b, : len(w)] = w
             if len(w) < Lmax:
-                stage[b, len(w):] = 0.0
-            lens[b] = len(w)
+                stage_np[b, len(w):] = 0.0
+        _parallel(put, B)
         # device-side buffers are cached per slot too: with every address stable, a repeated (batch, length) call is
         # replayed from a CUDA graph by the native library (include/ovc.h: OVC_OPT_GRAPH)
         wav = self._dev(f"wav{slot}", B * Lmax, torch.float32).view(B, Lmax)
@@ -567,7 +593,7 @@ class ToneColorConverter(OpenVoiceBaseClass):
         host.copy_(o, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         audio = host.numpy()
-        return [audio[b, : frames[b] * hop].copy() for b in range(len(waves))]
+        return _parallel(lambda b: audio[b, : frames[b] * hop].copy(), len(waves))
 
     @torch.no_grad()
     def convert_batch_device(self, audios: Sequence[AudioLike], src_se, tgt_se, tau: float = 0.3, slot: int = 0):

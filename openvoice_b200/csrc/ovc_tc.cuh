@@ -178,8 +178,8 @@ __device__ __forceinline__ void split_f16x8(float4 a, float4 b, float slope, uin
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float x0 = x[2 * i], x1 = x[2 * i + 1];
-    x0 = x0 > 0.f ? x0 : x0 * slope;
-    x1 = x1 > 0.f ? x1 : x1 * slope;
+    x0 = fmaxf(x0, x0 * slope);   // leaky_relu for 0 <= slope <= 1 (launch_tc checks), bit-identical to the select
+    x1 = fmaxf(x1, x1 * slope);
     const __half2 hh = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(hh);
     const __half2 ll = __floats2half2_rn((x0 - hf.x) * kLoScale, (x1 - hf.y) * kLoScale);

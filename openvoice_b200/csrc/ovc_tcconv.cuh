@@ -36,12 +36,15 @@ struct TcConvArgs {
   int epi;                             // 0 linear (bias, residual, accumulate, scale) | 1 WN gate | 2 WN res/skip
   int split; int first;                // EPI 2: columns < split update y (x += rs), the rest go to s[col - split] (= / +=)
   const long long* lens; int tmax; int mul;   // valid steps = min(tmax, lens[b]) * mul   (lens NULL -> tmax)
+  const long long* lens_x; int has_lens_x;    // when set: the INPUT's own validity limit (generator conv_pre on a padded batch:
+                                              // z_hat * y_mask is cut at the frame lengths, the output runs to tmax)
   int Cin; int Ntot; int K; int DIL;   // Ntot = output row width (C for a ResBlock conv, stride*Cout for a polyphase transposed conv)
   float slope; float scale; int accumulate;
   int passes;   // 3: split precision (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo); 1: single-pass fp16 (11-bit operands, like cuDNN's TF32 default)
   int act_tma;  // persistent kernel: 1 = activation chunks arrive by tensor-map TMA (box_rows x 32 channels, n_box boxes per
   int box_rows; //                    chunk), 0 = the converter warps load them from global memory themselves
   int n_box;
+  int tune;     // A/B switches (OVC_OPT_TUNE): bit 0 = L2 prefetch of the residual tile, bit 1 = two items per converter iteration
 };
 
 // one box of a [B][rows][Cin] fp32 tensor -> shared memory (128-byte swizzle), completion on an mbarrier
@@ -52,6 +55,17 @@ __device__ __forceinline__ void tma_tensor3d_g2s(void* dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+
+// ask the L2 for `bytes` (multiple of 16) starting at `p`: no destination, no completion -- the loads that follow hit L2
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Programmatic dependent launch (launch_tc sets the stream-serialization attribute): the NEXT kernel's CTAs may start
+// their prologue (barriers, TMEM, weight TMA) while this grid drains; a thread must pass pdl_wait() before it touches
+// anything the PREVIOUS kernel wrote (or overwrites anything it read).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -280,6 +294,7 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
   const int t0 = blockIdx.x * (MT * 128);
   const int n0 = blockIdx.y * TN;
   const int lim = (a.lens ? (int)min((long long)a.tmax, a.lens[b]) : a.tmax) * a.mul;
+  const int lim_x = a.has_lens_x ? (int)min((long long)a.tmax, a.lens_x[b]) * a.mul : lim;
   if (t0 >= lim) return;   // the tile lies past the utterance
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -299,6 +314,8 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
   __syncthreads();
   tc::fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();   // warp 0 only streams the (constant) weights: it may run ahead of the previous kernel's end
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer (TMA bulk)
@@ -375,7 +392,7 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
       for (int i = pt; i < pieces; i += 128) {
         const int row = i / NP, p = i % NP;
         const int t = t0 - H + row;
-        const bool ok = (t >= 0 && t < lim);
+        const bool ok = (t >= 0 && t < lim_x);
         const float* src = ok ? xb + (size_t)t * a.Cin + q * Cfg::KCH + p * 4 : xb;
         cp_async16_zfill(dst + (row * NP + (p ^ ((row >> 1) & 3))) * 16, src, ok ? 16 : 0);
       }
@@ -505,12 +522,16 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
   __syncthreads();
   tc::fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();   // warp 0 only streams the (constant) weights: it may run ahead of the previous kernel's end
 
   // every role walks the same tile sequence
 #define TCN_FOR_TILES                                                                                   \
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {                                        \
     const int b = tile / n_tt, t0 = (tile % n_tt) * (MT * 128);                                         \
     const int lim = (a.lens ? (int)min((long long)a.tmax, a.lens[b]) : a.tmax) * a.mul;                 \
+    const int lim_x = a.has_lens_x ? (int)min((long long)a.tmax, a.lens_x[b]) * a.mul : lim;            \
+    (void)lim_x;                                                                                        \
     if (t0 >= lim) continue;
 
   if (warp == 0) {
@@ -542,8 +563,21 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
       int st = 0;
       uint32_t phase = 1;   // the first pass finds every raw stage free
       const uint32_t box_bytes = (uint32_t)a.box_rows * 128u;
+      // the epilogue reads the residual (and the previous output when accumulating) of this tile long after its
+      // activations were requested: when the tile is contiguous in memory (one column tile: Ntot == TN == y_ld), pull it
+      // into L2 now, so that those loads -- few bytes in flight per warp -- pay L2 latency, not DRAM latency
+      const bool pf = (a.tune & 1) && a.epi == 0 && a.Ntot == TN && a.y_ld == TN && (a.r != nullptr || a.accumulate);
       TCN_FOR_TILES
-        (void)lim;
+        if (pf) {
+          const int rows = min(MT * 128, lim - t0);
+          const size_t off = ((size_t)b * a.y_bs + (size_t)t0 * TN) * sizeof(float);
+          const uint32_t bytes = (uint32_t)rows * TN * 4u;
+          for (uint32_t o = 0; o < bytes; o += 16384u) {
+            const uint32_t n = min(16384u, bytes - o);
+            if (a.r) l2_prefetch_bulk(reinterpret_cast<const char*>(a.r) + off + o, n);
+            if (a.accumulate) l2_prefetch_bulk(reinterpret_cast<const char*>(a.y) + off + o, n);
+          }
+        }
         for (int q = 0; q < nq; ++q) {
           mbar_wait(&raw_empty[st], phase);
           mbar_expect_tx(&raw_full[st], box_bytes * (uint32_t)a.n_box);
@@ -619,21 +653,43 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
         unsigned char* ah = abuf + buf * Cfg::A_BUF_BYTES;
         unsigned char* al = ah + NKC * ROWS * 16;
         if (act_tma) {
-          // raw stage, 128-byte swizzle: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4)
+          // raw stage, 128-byte swizzle: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4).
+          // Two items per iteration: both pairs of shared-memory loads are in flight before the first conversion
+          // (one item at a time left the LDS latency exposed: a single warp per scheduler runs this role).
           const unsigned char* rsrc = raw + st * Cfg::RAW_STAGE_BYTES;
-          for (int i = pt; i < items; i += 128) {
+          auto fetch = [&](int i, float4& v0, float4& v1) {
             const int row = i >> 2, kc = i & 3;
             const int t = t0 - H + row;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (t >= 0 && t < lim) {
+            v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            v1 = v0;
+            if (i < items && t >= 0 && t < lim_x) {
               const unsigned char* rr = rsrc + row * 128;
               v0 = *reinterpret_cast<const float4*>(rr + (((2 * kc) ^ (row & 7)) << 4));
               v1 = *reinterpret_cast<const float4*>(rr + (((2 * kc + 1) ^ (row & 7)) << 4));
             }
+          };
+          auto emit = [&](int i, const float4& v0, const float4& v1) {
+            if (i >= items) return;
+            const int row = i >> 2, kc = i & 3;
             uint4 hi, lo;
             tc::split_f16x8(v0, v1, a.slope, hi, lo);
             *reinterpret_cast<uint4*>(ah + (kc * ROWS + row) * 16) = hi;
             *reinterpret_cast<uint4*>(al + (kc * ROWS + row) * 16) = lo;
+          };
+          if (a.tune & 2) {
+            for (int i = pt; i < items; i += 256) {
+              float4 a0, a1, b0, b1;
+              fetch(i, a0, a1);
+              fetch(i + 128, b0, b1);
+              emit(i, a0, a1);
+              emit(i + 128, b0, b1);
+            }
+          } else {
+            for (int i = pt; i < items; i += 128) {
+              float4 a0, a1;
+              fetch(i, a0, a1);
+              emit(i, a0, a1);
+            }
           }
         } else {
           constexpr int PB = 5;   // items (32 bytes each) in flight per thread
@@ -646,7 +702,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
               const int t = t0 - H + row;
               v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
               v1[u] = v0[u];
-              if (i < items && t >= 0 && t < lim) {
+              if (i < items && t >= 0 && t < lim_x) {
                 const float4* src = reinterpret_cast<const float4*>(xb + (size_t)t * a.Cin + q * Cfg::KCH + kc * 8);
                 v0[u] = src[0];
                 v1[u] = src[1];
