@@ -42,7 +42,16 @@ sys.path.insert(0, ROOT)
 SR = 22050
 HOP = 256
 GFLOP_PER_FRAME = 0.65766          # 657.66 MFLOP per spectrogram frame
-FFMA_PEAK_TFLOPS = 74.4            # nominal 148 SM x 128 lanes x 2 x 1.965 GHz
+FFMA_PEAK_TFLOPS = 74.4            # nominal 148 SM x 128 lanes x 2 x 1.965 GHz (fallback)
+
+
+def ffma_peak():
+    """fp32 FMA peak of this pool's B200s as tools/ffma_bench.cu measured it (profiles/r02_ffma_peak.json), else nominal"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ffma_peak.json")))
+        return float(d["ffma_peak_tflops"]), "measured (tools/ffma_bench.cu, profiles/r02_ffma_peak.json)"
+    except Exception:
+        return FFMA_PEAK_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
 
 
 def synth_wave(i, secs):
@@ -526,8 +535,8 @@ def main():
             "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
             "avg_launch_ms": k_ms, "launches": prof["launches"], "share_of_step": prof["ms"] / args.steps / ms_prof_step,
             "binding": "fp32 FFMA (dense contraction, SURVEY.md section 8d)",
-            "ffma": {"achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FFMA_PEAK_TFLOPS,
-                     "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"},
+            "ffma": {"achieved": ach_tf, "peak": ffma_peak()[0], "unit": "TFLOP/s", "frac": ach_tf / ffma_peak()[0],
+                     "peak_source": ffma_peak()[1]},
         }
     else:
         # tensor-core modes.  achieved = ALGORITHMIC FLOPs (2*MAC of the reference's convs) / CUDA-event time; the split

@@ -966,7 +966,7 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   const double units = (double)r.B * t_len;
   const int eff_k = family == 2 ? 2 : T.K;   // polyphase transposed conv: 2 of the 3 packed taps are non-zero per row
   TRY(prof_end(r, T.TN == 128 ? V_TC128 : T.TN == 64 ? V_TC64 : V_TC32, family == 1 ? 1 : 0, 2.0 * T.Cin * T.Ntot * eff_k * units,
-               4.0 * (T.Cin + T.Ntot) * units, (T.Cin << 16) | (T.K << 8) | T.DIL));
+               4.0 * (T.Cin + T.Ntot * (1 + (res ? 1 : 0) + (accumulate ? 1 : 0))) * units, (T.Cin << 16) | (T.K << 8) | T.DIL));
   return OVC_OK;
 }
 

@@ -17,6 +17,22 @@ __global__ void __launch_bounds__(256) k(float* out, int iters, float seed) {
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int i = 0; i < 16; ++i) c[i] = fmaf(a[(i + r) & 15], b[(i * 3 + r) & 15], c[i]);
+    } else if (MODE == 2) {
+      // peak issue rate: one operand is shared by the 16 independent chains (register reuse cache), 64 FFMA
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fmaf(c[i], a[r], b[r]);
+    } else if (MODE == 3) {
+      // packed peak: 64 FFMA2 whose multiplier pair is shared by the 8 chains of a round
+      unsigned long long* a2 = reinterpret_cast<unsigned long long*>(a);
+      unsigned long long* b2 = reinterpret_cast<unsigned long long*>(b);
+      unsigned long long* c2 = reinterpret_cast<unsigned long long*>(c);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c2[i]) : "l"(a2[r]), "l"(b2[r]));
     } else {
       unsigned long long* a2 = reinterpret_cast<unsigned long long*>(a);
       unsigned long long* b2 = reinterpret_cast<unsigned long long*>(b);
@@ -55,5 +71,7 @@ void run(const char* name, int fma_per_iter) {
 int main() {
   run<0>("FFMA  (3 fresh regs)", 64);
   run<1>("FFMA2 (3 fresh pairs)", 128);
+  run<2>("FFMA  peak (shared multiplier, 16 chains)", 64);
+  run<3>("FFMA2 peak (shared multiplier pair, 8 chains)", 128);
   return 0;
 }

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Target process for ncu captures: `calls` convert_waveform calls of batch x secs synthetic clips (default f16x3 mode).
 
-Tensor-core conv launches of ONE call, in order (172): enc WN 32, flow fwd 32, flow rev 32, then the generator:
-ups0, stage0 x18, ups1, stage1 x18, ups2, stage2 x18, ups3, stage3 x18 (within a stage: k=3 | 7 | 11, each
-c1(d1) c2 c1(d3) c2 c1(d5) c2).  See tools/gpu_ncu.sh for the -s / -c arithmetic."""
+Tensor-core conv launches of ONE call, in order (173): enc WN 32, flow fwd 32, flow rev 32, then the generator:
+conv_pre [96], ups0 [97], stage0 [98..115], ups1 [116], stage1 [117..134], ups2 [135], stage2 [136..153], ups3 [154],
+stage3 [155..172] (within a stage: k=3 | 7 | 11, each c1(d1) c2 c1(d3) c2 c1(d5) c2).  A call launches 214 kernels in all
+(213 + the call-parameter kernel).  See tools/gpu_ncu.sh for the -s / -c arithmetic."""
 import argparse
 import json
 import os

@@ -88,8 +88,8 @@ def dram(path, out, batch="32"):
         v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(unit, 1.0)
         per.setdefault(i, {"kernel": row["Kernel Name"].split("(")[0]})[row["Metric Name"]] = v
     ids = sorted(per)
-    assert len(ids) == 172, f"expected the 172 tensor-core conv launches of one call, got {len(ids)}"
-    stages = {"stage0_C256": range(97, 115), "stage1_C128": range(116, 134), "stage2_C64": range(135, 153), "stage3_C32": range(154, 172)}
+    assert len(ids) == 173, f"expected the 173 tensor-core conv launches of one call, got {len(ids)}"
+    stages = {"stage0_C256": range(98, 116), "stage1_C128": range(117, 135), "stage2_C64": range(136, 154), "stage3_C32": range(155, 173)}
     res = {"what": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none (single pass, no "
                    f"replay), one convert call at batch {batch} x 10 s, f16x3; the 72 generator ResBlock conv launches", "stages": {}}
     tot_b, tot_ms = 0.0, 0.0
