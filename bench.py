@@ -155,6 +155,14 @@ def cpu_reference_throughput(n_clips, secs, threads=None, budget_s=25.0):
     return audio_s / dt, dt, torch.get_num_threads(), len(done)
 
 
+def workload_config(B, secs, world):
+    """the `config` object both arms report: BASELINE.json configs[1] unless --batch / --secs say otherwise"""
+    T = int(round(secs * SR)) // HOP
+    return {"workload": f"ToneColorConverter.convert_batch, batch {B} x {secs:g} s clips @ {SR} Hz per GPU "
+                        "(BASELINE configs[1]), seeded synthetic checkpoint, tau 0.3, in-kernel Philox noise",
+            "batch_per_gpu": B, "global_batch": B * world, "secs": secs, "frames": T}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -173,8 +181,9 @@ def run_reference(args):
         "impl": "reference", "metric": "audio_seconds_per_second", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ToneColorConverter.convert, {args.secs:g} s clips @ {SR} Hz (bounded sample of the batch-{args.batch} workload)",
-                   "batch": n_clips, "secs": args.secs},
+        "config": dict(workload_config(args.batch, args.secs, args.gpus),
+                       sample=f"each step converts {n_clips} of the {args.batch} clips (bounded sample; the metric is a rate)",
+                       parallelism=f"{threads} host threads", e2e_api="oracle port of ToneColorConverter.convert (torch CPU)"),
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -567,11 +576,9 @@ def main():
         "dtype": {"fp32": "f32", "f16x3": "f32 (3xFP16 split-precision tensor-core convs with fp32 accumulation, fp32 FFMA2 elsewhere)",
                   "f16": "f16 operands, f32 accumulation (single-pass tensor-core convs, fp32 elsewhere)"}[args.precision],
         "data": "synthetic", "precision": args.precision, "modes_audio_s_per_s": modes,
-        "config": {"workload": f"ToneColorConverter.convert_batch, batch {B} x {secs:g} s clips @ {SR} Hz per GPU "
-                               "(BASELINE configs[1]), seeded synthetic checkpoint, tau 0.3, in-kernel Philox noise",
-                   "batch_per_gpu": B, "global_batch": B * world, "secs": secs, "frames": T,
-                   "l2": "activations per step (>3 GB) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": f"replicas x{world}", "e2e_api": e2e_api},
+        "config": dict(workload_config(B, secs, world),
+                       l2="activations per step (>3 GB) exceed the 126 MB L2; no explicit flush",
+                       parallelism=f"replicas x{world}", e2e_api=e2e_api),
         "tflops_algorithmic": world * B * T * GFLOP_PER_FRAME / ms_dev,
         "e2e": {"value": e2e_val, "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

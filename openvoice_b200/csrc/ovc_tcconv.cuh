@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(TcwCfg<MT>::THREADS, TcwCfg<MT>::MINB) tcconv_
 //               engine -- the copy engine, not registers, holds the bytes in flight (the narrow layers are HBM-bound:
 //               a whole tile must be in flight per SM to cover the latency).  [Measured: one 128-byte bulk copy per
 //               row instead costs ~55 cycles of TMA issue each and caps the kernel at 1.1 TB/s.]
-//   warps 3-6   converters: raw stage (or, act_tma = 0, global memory) -> lrelu -> fp16 hi/lo split -> operand
+//   warps 3-6   (2-6 when TN = 128: its second MMA-issuer warp is free) converters: raw stage (or, act_tma = 0, global
+//               memory) -> lrelu -> fp16 hi/lo split -> operand
 //               layout; rows outside the utterance become zeros here (zero padding, x_mask and the ragged batch in
 //               one rule)
 //   warp 0      weight TMA; warps 1-2 one MMA-issuing thread each (TN = 128: one)
@@ -459,6 +460,8 @@ template <int TN>
 struct TcnCfg {
   static constexpr int MT = TN == 128 ? 1 : 2;                    // 2 sets x MT x (main + low-order) x TN <= 512 TMEM columns
   static constexpr int NISS = MT >= 2 ? 2 : 1;
+  static constexpr int CONV_W0 = 1 + NISS;                        // first converter warp: with one MMA issuer (TN = 128) warp 2
+  static constexpr int NCT = (7 - CONV_W0) * 32;                  // joins the converters (5 warps instead of 4)
   static constexpr int KCH = 32, NKC = KCH / 8, KS = KCH / 16;
   static constexpr int ROWS = MT * 128 + 66;                      // = 2 (mod 8)
   static constexpr int RAW_ROWS = MT == 1 ? 184 : 320;            // tile + 2 * 25 halo, rounded up to 8 (16 when two boxes)
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
                                                                 const __grid_constant__ CUtensorMap tmap) {
   using Cfg = TcnCfg<TN>;
   constexpr int MT = Cfg::MT, ROWS = Cfg::ROWS, NABUF = Cfg::NABUF, RING = Cfg::RING, NKC = Cfg::NKC, NRAW = Cfg::NRAW,
-                NISS = Cfg::NISS;
+                NISS = Cfg::NISS, NCT = Cfg::NCT;
   constexpr uint32_t SET_COLS = 2 * MT * TN;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -511,10 +514,10 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
   constexpr uint32_t BYTES = Cfg::SLOT_BYTES;
 
   if (tid == 0) {
-    for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], NISS); }
+    for (int i = 0; i < NABUF; ++i) { mbar_init(&a_full[i], NCT); mbar_init(&a_empty[i], NISS); }
     for (int i = 0; i < RING; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NISS); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], NISS); mbar_init(&acc_empty[i], 8); }
-    for (int i = 0; i < NRAW; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 128); }
+    for (int i = 0; i < NRAW; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], NCT); }
     fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -639,9 +642,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
         ++n;
       }
     }
-  } else if (warp >= 3 && warp <= 6) {
+  } else if (warp >= Cfg::CONV_W0 && warp <= 6) {
     // ------------------------------------------------------------ converters (run ahead across tiles)
-    const int pt = tid - 96;
+    const int pt = tid - 32 * Cfg::CONV_W0;
     const int items = rows8 * NKC;            // item i = (row i / 4, column block i % 4): 32 bytes of one row
     int buf = 0, st = 0;
     uint32_t ephase = 1, rphase = 0;
@@ -677,15 +680,15 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
             *reinterpret_cast<uint4*>(al + (kc * ROWS + row) * 16) = lo;
           };
           if (a.tune & 2) {
-            for (int i = pt; i < items; i += 256) {
+            for (int i = pt; i < items; i += 2 * NCT) {
               float4 a0, a1, b0, b1;
               fetch(i, a0, a1);
-              fetch(i + 128, b0, b1);
+              fetch(i + NCT, b0, b1);
               emit(i, a0, a1);
-              emit(i + 128, b0, b1);
+              emit(i + NCT, b0, b1);
             }
           } else {
-            for (int i = pt; i < items; i += 128) {
+            for (int i = pt; i < items; i += NCT) {
               float4 a0, a1;
               fetch(i, a0, a1);
               emit(i, a0, a1);
@@ -693,11 +696,11 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
           }
         } else {
           constexpr int PB = 5;   // items (32 bytes each) in flight per thread
-          for (int i0 = pt; i0 < items; i0 += 128 * PB) {
+          for (int i0 = pt; i0 < items; i0 += NCT * PB) {
             float4 v0[PB], v1[PB];
 #pragma unroll
             for (int u = 0; u < PB; ++u) {
-              const int i = i0 + 128 * u;
+              const int i = i0 + NCT * u;
               const int row = i >> 2, kc = i & 3;
               const int t = t0 - H + row;
               v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -710,7 +713,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
             }
 #pragma unroll
             for (int u = 0; u < PB; ++u) {
-              const int i = i0 + 128 * u;
+              const int i = i0 + NCT * u;
               if (i >= items) break;
               const int row = i >> 2, kc = i & 3;
               uint4 hi, lo;

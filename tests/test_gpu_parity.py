@@ -404,6 +404,14 @@ def test_streaming_equals_whole_clip(tmp_path, synthetic_sd):
         # state: at most the two halos, one window and the frames of the largest chunk; audio tail of a few frames
         assert max_frames <= W + 2 * 128 + max(sizes) // 256 + 8, max_frames
         assert max_samples <= max(sizes) + 2048, max_samples
+    # a stream shorter than one window + halo: nothing comes out before flush, and flush returns the whole clip
+    Ls = 22050 + 5
+    short = conv.convert(wav[:Ls], src, tgt, tau=0.3, noise=noise[None, :, : Ls // 256])
+    sc = StreamingConverter(conv, src, tgt, tau=0.3, window_frames=200, noise_fn=lambda a, b: noise[:, a:b])
+    early = [sc.push(wav[p: min(Ls, p + 5000)]) for p in range(0, Ls, 5000)]
+    assert sum(len(e) for e in early) == 0
+    tail = sc.flush()
+    assert tail.shape == short.shape and rel_err(tail, short) <= 2e-6
 
 
 def test_api_convert_matches_reference_golden(tmp_path, synthetic_sd):
