@@ -141,6 +141,14 @@ def test_graph_replay_is_bit_identical(native):
     nat.set_option("graph", 0)
     e = call(9)
     assert torch.equal(e, ref9) and nat.last_launch_count == launches
+    # the concurrent-branch schedule of small calls (three streams, a third of the SMs per kernel) keeps the MRF
+    # accumulation order: same bits as the sequential schedule, directly launched and replayed
+    nat.set_option("branches", 0)
+    seq = call(9)
+    nat.set_option("graph", 1)
+    seq_g = [call(9) for _ in range(3)][-1]
+    nat.set_option("branches", 1)
+    assert torch.equal(seq, ref9) and torch.equal(seq_g, ref9)
 
 
 def test_flow_roundtrip_property_full_size(native):
