@@ -130,6 +130,29 @@ def host_cores():
     return max(1, min(n, 64))
 
 
+def pin_to_gpu_numa(local):
+    """Multi-rank runs: keep this rank's host threads (staging copies, NCCL proxy) on the NUMA node its GPU hangs off.
+    Best effort: returns a short description, or None when sysfs does not say."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception:
+        return None
+
+
 def cpu_reference_throughput(n_clips, secs, threads=None, budget_s=25.0):
     """Time the oracle port of the reference's convert() arithmetic (spectrogram + voice_conversion,
     batch 1 per utterance like openvoice/api.py:141-155) on the host cores."""
@@ -317,6 +340,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa = pin_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun"
@@ -348,8 +372,11 @@ def main():
     wav_dev = torch.from_numpy(np.stack(waves)).to(dev)
     wav_len = torch.full((B,), L, dtype=torch.int64, device=dev)
 
-    def device_step(seed):
-        o, _ = conv.model.native.convert_waveform(wav_dev, wav_len, src, tgt, tau=0.3, seed=seed)
+    out_dev = torch.empty(B, T * HOP, device=dev)
+    frames_dev = torch.empty(B, dtype=torch.int64, device=dev)
+
+    def device_step(seed):      # every buffer at a stable address: the library replays the call from a CUDA graph
+        o, _ = conv.model.native.convert_waveform(wav_dev, wav_len, src, tgt, tau=0.3, seed=seed, out=out_dev, frames_out=frames_dev)
         return o
 
     def barrier():
@@ -578,7 +605,7 @@ def main():
         "data": "synthetic", "precision": args.precision, "modes_audio_s_per_s": modes,
         "config": dict(workload_config(B, secs, world),
                        l2="activations per step (>3 GB) exceed the 126 MB L2; no explicit flush",
-                       parallelism=f"replicas x{world}", e2e_api=e2e_api),
+                       parallelism=f"replicas x{world}" + (f", rank 0 pinned to {numa}" if numa else ""), e2e_api=e2e_api),
         "tflops_algorithmic": world * B * T * GFLOP_PER_FRAME / ms_dev,
         "e2e": {"value": e2e_val, "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

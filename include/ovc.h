@@ -185,9 +185,10 @@ OVC_API int ovc_set_precision(ovc_ctx* ctx, int mode);
  *   OVC_OPT_ACT_TMA       1 (default): the persistent conv kernel receives its activation tiles by tensor-map TMA;
  *                         0: its converter warps load them from global memory
  *   OVC_OPT_GRAPH         1 (default): replay the launch sequence of a repeated (shape, buffers) call from a CUDA graph
- *   OVC_OPT_PDL           1: the tensor-core conv kernels are launched with programmatic stream serialization: the prologue
- *                         of kernel n+1 (barriers, TMEM, weight TMA) overlaps the drain of kernel n.  Default 0: measured
- *                         on a B200 it saves 8 % of a batch-1 call without graph replay (0.6 % with) and costs 3 % at batch 32 */
+ *   OVC_OPT_PDL           programmatic stream serialization of the tensor-core conv launches (the prologue of kernel n+1 --
+ *                         barriers, TMEM, weight TMA -- overlaps the drain of kernel n): 0 off, 1 all of them, 2 (default)
+ *                         the WaveNet stacks only.  Measured on a B200: 2 saves 0.5-0.8 % at batch 32 and 2.4 % at batch 1;
+ *                         1 costs 3 % at batch 32 */
 #define OVC_OPT_WIDE_VARIANT 1
 #define OVC_OPT_TTS_SIMPLE 2
 #define OVC_OPT_GRAPH 3

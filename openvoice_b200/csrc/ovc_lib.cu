@@ -192,7 +192,9 @@ struct ovc_ctx {
   bool act_tma = true;         // OVC_OPT_ACT_TMA
   bool tts_simple = false;     // OVC_OPT_TTS_SIMPLE
   bool use_graph = true;       // OVC_OPT_GRAPH
-  bool use_pdl = false;        // OVC_OPT_PDL (measured: -8 % at batch 1 without graphs, +3 % at batch 32)
+  int use_pdl = 2;             // OVC_OPT_PDL: 0 off, 1 every tensor-core conv, 2 (default) the WaveNet stacks only -- short kernels
+                               // whose fill / drain dominates (measured: 2 gives -0.5 .. -0.8 % at batch 32 and -2.4 % at
+                               // batch 1; 1 gives +3 % at batch 32)
   int tune = 2;                // OVC_OPT_TUNE (TcConvArgs.tune)
   // small calls: the three ResBlock branches of an MRF stage run concurrently on three streams, each kernel on a third
   // of the SMs (OVC_OPT_BRANCHES; taken when B * Tmax <= par_frames = 512 frames: measured -8 % at 258 frames, +2 % at 861)
@@ -940,8 +942,9 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
     // A/B alternatives of the 128-column layers: 1 = 256-step tiles, one CTA per SM; 2 = 128-step tiles, two CTAs per SM
     const int MT = wv == 1 ? 2 : 1;
     dim3 grid((t_len + MT * 128 - 1) / (MT * 128), T.Ntot / 128, r.B);
-    if (wv == 1) CK(launch_ex(tcconv_wide_kernel<2>, grid, TcwCfg<2>::THREADS, TcwCfg<2>::SMEM_BYTES, r.st, r.c->use_pdl, a));
-    else CK(launch_ex(tcconv_wide_kernel<1>, grid, TcwCfg<1>::THREADS, TcwCfg<1>::SMEM_BYTES, r.st, r.c->use_pdl, a));
+    const bool pdl = r.c->use_pdl == 1 || (r.c->use_pdl == 2 && ex.epi != 0);
+    if (wv == 1) CK(launch_ex(tcconv_wide_kernel<2>, grid, TcwCfg<2>::THREADS, TcwCfg<2>::SMEM_BYTES, r.st, pdl, a));
+    else CK(launch_ex(tcconv_wide_kernel<1>, grid, TcwCfg<1>::THREADS, TcwCfg<1>::SMEM_BYTES, r.st, pdl, a));
   } else {
     // persistent: one CTA per SM walks the (utterance, tile) list; column tiles (if any) on grid.y
     const int MT = T.TN == 128 ? TcnCfg<128>::MT : TcnCfg<64>::MT;
@@ -970,7 +973,7 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
     const int ncol = T.Ntot / T.TN;
     const int per_col = std::max(1, r.c->sm_count / ncol / std::max(1, ex.grid_div));
     dim3 pg((unsigned)std::min(total, per_col), ncol, 1);
-    const bool pdl = r.c->use_pdl;
+    const bool pdl = r.c->use_pdl == 1 || (r.c->use_pdl == 2 && ex.epi != 0);
     if (T.TN == 128) CK(launch_ex(tcconv_kernel<128>, pg, TCN_THREADS, TcnCfg<128>::SMEM_BYTES, r.st, pdl, a, n_tt, total, tmap));
     else if (T.TN == 64) CK(launch_ex(tcconv_kernel<64>, pg, TCN_THREADS, TcnCfg<64>::SMEM_BYTES, r.st, pdl, a, n_tt, total, tmap));
     else CK(launch_ex(tcconv_kernel<32>, pg, TCN_THREADS, TcnCfg<32>::SMEM_BYTES, r.st, pdl, a, n_tt, total, tmap));
@@ -1154,7 +1157,7 @@ static int set_call_params(ovc_ctx* c, uint64_t seed, float tau, cudaStream_t st
   return OVC_OK;
 }
 static uintptr_t option_bits(const ovc_ctx* c) {
-  return (uintptr_t)c->precision | ((uintptr_t)c->wide_variant << 4) | ((uintptr_t)c->act_tma << 8) | ((uintptr_t)c->use_pdl << 9) | ((uintptr_t)c->tune << 10) | ((uintptr_t)c->use_branches << 14);
+  return (uintptr_t)c->precision | ((uintptr_t)c->wide_variant << 4) | ((uintptr_t)c->act_tma << 8) | ((uintptr_t)c->use_pdl << 15) | ((uintptr_t)c->tune << 10) | ((uintptr_t)c->use_branches << 14);
 }
 
 static int ensure_ws(ovc_ctx* c, const WsLayout& W, int B, int Tmax, cudaStream_t st) {
@@ -1694,7 +1697,10 @@ int ovc_set_option(ovc_ctx* c, int key, int value) {
     case OVC_OPT_TTS_SIMPLE: c->tts_simple = value != 0; return OVC_OK;
     case OVC_OPT_GRAPH: c->use_graph = value != 0; return OVC_OK;
     case OVC_OPT_ACT_TMA: c->act_tma = value != 0; return OVC_OK;
-    case OVC_OPT_PDL: c->use_pdl = value != 0; return OVC_OK;
+    case OVC_OPT_PDL:
+      if (value < 0 || value > 2) return fail(OVC_ERR_INVALID, "pdl must be 0, 1 or 2");
+      c->use_pdl = value;
+      return OVC_OK;
     case OVC_OPT_TUNE: c->tune = value; return OVC_OK;
     case OVC_OPT_BRANCHES: c->use_branches = value != 0; return OVC_OK;
     default: return fail(OVC_ERR_INVALID, "unknown option %d", key);
