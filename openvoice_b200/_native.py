@@ -198,7 +198,7 @@ class NativeConverter:
 
     def set_option(self, key: str, value: int):
         """Tuning switches of include/ovc.h: 'wide_variant' (0/1/2/3), 'tts_simple' (0/1), 'graph' (0/1), 'act_tma' (0/1), 'pdl' (0/1)."""
-        k = {"wide_variant": 1, "tts_simple": 2, "graph": 3, "act_tma": 4, "pdl": 5, "tune": 6, "branches": 7}[key]
+        k = {"wide_variant": 1, "tts_simple": 2, "graph": 3, "act_tma": 4, "pdl": 5, "tune": 6, "branches": 7, "pair": 8}[key]
         _check(self.lib, self.lib.ovc_set_option(self.handle, k, int(value)), "ovc_set_option")
 
     # ---- hot path --------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 #include "../../include/ovc.h"
 #include "ovc_small.cuh"
 #include "ovc_tcconv.cuh"
+#include "ovc_tcpair.cuh"
 #include "ovc_tts.cuh"
 #include "ovc_refenc.cuh"
 #include "ovc_variants.h"
@@ -200,6 +201,7 @@ struct ovc_ctx {
   // of the SMs (OVC_OPT_BRANCHES; taken when B * Tmax <= par_frames = 512 frames: measured -8 % at 258 frames, +2 % at 861)
   bool use_branches = true;
   int par_frames = 512;
+  bool use_pair = true;        // OVC_OPT_PAIR: the HBM-bound ResBlock conv pairs (C <= 64, k = 3) as ONE kernel (ovc_tcpair.cuh)
   cudaStream_t br_stream[2] = {nullptr, nullptr};
   cudaEvent_t br_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t post_w_off = 0;
@@ -712,6 +714,8 @@ static int finalize(ovc_ctx* c) {
   CK(cudaFuncSetAttribute(tcconv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<128>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tcconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<64>::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tcconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcnCfg<32>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcpair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcpCfg<32>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tcpair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcpCfg<64>::SMEM_BYTES));
   if (c->d_cond_wrow) cudaFree(c->d_cond_wrow);
   if (c->d_cond_sel) cudaFree(c->d_cond_sel);
   CK(cudaMalloc(&c->d_cond_wrow, wrow.size() * sizeof(int)));
@@ -866,11 +870,13 @@ static int prof_end(Run& r, int variant, int family, double flops, double bytes,
   c->ev_tag.push_back(tag);
   return OVC_OK;
 }
-enum { V_TC128 = -1, V_TC64 = -2, V_TC32 = -3, V_TRANSPOSE = -4, V_TTS_DENSE = -5, V_TTS_LN = -6, V_TTS_SCORES = -7,
+enum { V_TCPAIR64 = -12, V_TCPAIR32 = -13, V_TC128 = -1, V_TC64 = -2, V_TC32 = -3, V_TRANSPOSE = -4, V_TTS_DENSE = -5, V_TTS_LN = -6, V_TTS_SCORES = -7,
        V_TTS_ATTN = -8, V_TTS_DW = -9, V_TTS_SPLINE = -10, V_TTS_MISC = -11 };
 static const char* variant_name(int v) {
   if (v >= 0) return kInfo[v].name;
   switch (v) {
+    case V_TCPAIR64: return "PAIR_N64";
+    case V_TCPAIR32: return "PAIR_N32";
     case V_TC128: return "TC3_N128";
     case V_TC64: return "TC3_N64";
     case V_TC32: return "TC3_N32";
@@ -984,6 +990,55 @@ static int launch_tc(Run& r, const TcLayer& T, const float* x, float* y, const f
   const int eff_k = family == 2 ? 2 : T.K;   // polyphase transposed conv: 2 of the 3 packed taps are non-zero per row
   TRY(prof_end(r, T.TN == 128 ? V_TC128 : T.TN == 64 ? V_TC64 : V_TC32, family == 1 ? 1 : 0, 2.0 * T.Cin * T.Ntot * eff_k * units,
                4.0 * (T.Cin + T.Ntot * (1 + (res ? 1 : 0) + (accumulate ? 1 : 0))) * units, (T.Cin << 16) | (T.K << 8) | T.DIL));
+  return OVC_OK;
+}
+
+// one ResBlock conv pair (c1 dilated, c2 dilation 1, residual = the pair's input) as ONE kernel: C = 64 / 32 stages
+// Only where BOTH convs' weights stay resident in shared memory next to the operand tiles, and only the HBM-bound pairs:
+// C = 32 and C = 64 at k <= 5 / k = 3.  Measured (C = 32, per pair, 32 x 10 s): k = 3 -25 %, k = 7 equal, k = 11 +8 % (those are
+// bound by shared-memory operand reads, not HBM, and pay for the 118 / 128 tile efficiency).
+static bool pair_fits(const TcLayer& T1, const TcLayer& T2) {
+  if (!(T1.TN == 32 || T1.TN == 64)) return false;
+  const int ring = T1.TN == 32 ? TcpCfg<32>::RING : TcpCfg<64>::RING, hmax = T1.TN == 32 ? TcpCfg<32>::HMAX : TcpCfg<64>::HMAX;
+  return T1.Ntot == T1.TN && T1.Cin == T1.TN && T2.Ntot == T1.TN && T2.Cin == T1.TN && T2.TN == T1.TN && T2.K == T1.K &&
+         T2.DIL == 1 && (T1.K - 1) / 2 * T1.DIL <= hmax && 2 * (T1.Cin / 16) * T1.K <= ring && T1.K <= 5;
+}
+static int launch_pair(Run& r, const TcLayer& T1, const TcLayer& T2, const float* x, float* y, int t_len, int mul, float slope,
+                       float scale, int accumulate) {
+  TcPairArgs a{};
+  const int C = T1.TN;
+  a.x = x; a.x_bs = (long long)C * r.P * mul;
+  a.w1 = reinterpret_cast<const uint16_t*>(r.c->d_tcw + T1.w_off);
+  a.w2 = reinterpret_cast<const uint16_t*>(r.c->d_tcw + T2.w_off);
+  a.bias1 = r.c->d_tcw + T1.b_off; a.bias2 = r.c->d_tcw + T2.b_off;
+  a.y = y; a.y_bs = a.x_bs;
+  a.lens = r.glens; a.tmax = r.Tmax; a.mul = mul;
+  a.C = C; a.K = T1.K; a.DIL1 = T1.DIL;
+  a.slope = slope; a.scale = scale; a.accumulate = accumulate;
+  a.passes = r.c->precision == 2 ? 1 : 3;
+  if (!encode_tiled_fn()) return fail(OVC_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  const int H1 = (T1.K - 1) / 2 * T1.DIL, H2 = (T1.K - 1) / 2;
+  const int R = 128 - 2 * H2, rows8 = (128 + 2 * H1 + 7) & ~7;
+  const int n_tt = (t_len + R - 1) / R, total = n_tt * r.B;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof tmap);
+  const cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)r.P * mul, (cuuint64_t)r.B};
+  const cuuint64_t gstr[2] = {(cuuint64_t)C * 4, (cuuint64_t)a.x_bs * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)rows8, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult cr = encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(OVC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a conv pair", (int)cr);
+  TRY(prof_begin(r));
+  dim3 pg((unsigned)std::min(total, r.c->sm_count), 1, 1);
+  if (C == 64) CK(launch_ex(tcpair_kernel<64>, pg, TCN_THREADS, TcpCfg<64>::SMEM_BYTES, r.st, false, a, n_tt, total, tmap));
+  else CK(launch_ex(tcpair_kernel<32>, pg, TCN_THREADS, TcpCfg<32>::SMEM_BYTES, r.st, false, a, n_tt, total, tmap));
+  CK(cudaGetLastError());
+  r.c->launches++;
+  const double units = (double)r.B * t_len;
+  TRY(prof_end(r, C == 64 ? V_TCPAIR64 : V_TCPAIR32, 1, 2.0 * 2.0 * C * C * T1.K * units, 4.0 * C * (2 + (accumulate ? 1 : 0)) * units,
+               (C << 16) | (T1.K << 8) | T1.DIL));
   return OVC_OK;
 }
 
@@ -1157,7 +1212,7 @@ static int set_call_params(ovc_ctx* c, uint64_t seed, float tau, cudaStream_t st
   return OVC_OK;
 }
 static uintptr_t option_bits(const ovc_ctx* c) {
-  return (uintptr_t)c->precision | ((uintptr_t)c->wide_variant << 4) | ((uintptr_t)c->act_tma << 8) | ((uintptr_t)c->use_pdl << 15) | ((uintptr_t)c->tune << 10) | ((uintptr_t)c->use_branches << 14);
+  return (uintptr_t)c->precision | ((uintptr_t)c->wide_variant << 4) | ((uintptr_t)c->act_tma << 8) | ((uintptr_t)c->use_pdl << 15) | ((uintptr_t)c->tune << 10) | ((uintptr_t)c->use_branches << 14) | ((uintptr_t)c->use_pair << 17);
 }
 
 static int ensure_ws(ovc_ctx* c, const WsLayout& W, int B, int Tmax, cudaStream_t st) {
@@ -1246,14 +1301,27 @@ static int run_dec(Run& r, const WsLayout& W, float* ws, const float* cond, cons
       snprintf(nm, sizeof nm, "dec.ups%d", i);
       TRY(tap_cl(nm, bufA, cout, Tlen, pitch_out));
       if (!par) {
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < 3; ++j) {
+          bool fused = c->use_pair;
+          for (int d = 0; d < 3; ++d) fused = fused && pair_fits(c->tc_c1[i * 3 + j][d], c->tc_c2[i * 3 + j][d]);
+          if (fused) {
+            // one kernel per conv pair; a pair never runs in place (its tiles read x with a halo), so the running
+            // activation ping-pongs bufA -> bufB -> bufC -> bufD (bufC is free: the intermediate stays on chip)
+            const float* xs[3] = {bufA, bufB, bufC};
+            float* ys[3] = {bufB, bufC, bufD};
+            for (int d = 0; d < 3; ++d)
+              TRY(launch_pair(r, c->tc_c1[i * 3 + j][d], c->tc_c2[i * 3 + j][d], xs[d], ys[d], Tlen, up_out, 0.1f,
+                              (d == 2 && j == 2) ? 1.0f / 3.0f : 1.f, (d == 2 && j > 0) ? 1 : 0));
+            continue;
+          }
           for (int d = 0; d < 3; ++d) {
             const float* xin = d == 0 ? bufA : bufB;
-            TRY(launch_tc(r, c->tc_c1[i * 3 + j][d], xin, bufC, nullptr, Tlen, up_out, 0.1f, 1.f, 0, 1));
             float* yout = d < 2 ? bufB : bufD;
+            TRY(launch_tc(r, c->tc_c1[i * 3 + j][d], xin, bufC, nullptr, Tlen, up_out, 0.1f, 1.f, 0, 1));
             TRY(launch_tc(r, c->tc_c2[i * 3 + j][d], bufC, yout, xin, Tlen, up_out, 0.1f,
                           (d == 2 && j == 2) ? 1.0f / 3.0f : 1.f, (d == 2 && j > 0) ? 1 : 0, 1));
           }
+        }
       } else {
         // a latency-bound call: the three ResBlock branches (models.py:280-285) are independent up to their last conv,
         // so they run side by side -- branch 0 on the caller's stream, 1 and 2 on side streams, every kernel on a third
@@ -1703,6 +1771,7 @@ int ovc_set_option(ovc_ctx* c, int key, int value) {
       return OVC_OK;
     case OVC_OPT_TUNE: c->tune = value; return OVC_OK;
     case OVC_OPT_BRANCHES: c->use_branches = value != 0; return OVC_OK;
+    case OVC_OPT_PAIR: c->use_pair = value != 0; return OVC_OK;
     default: return fail(OVC_ERR_INVALID, "unknown option %d", key);
   }
 }
@@ -1757,7 +1826,8 @@ int ovc_profile_detail(ovc_ctx* c, int max, char* names /* max x 16 */, double* 
     CK(cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]));
     if (names) {
       const int tag = c->ev_tag[i / 2], v = c->ev_variant[i / 2];
-      if (tag) snprintf(names + 16 * n, 16, "T%dc%dk%dd%d", v == V_TC128 ? 128 : v == V_TC64 ? 64 : 32, tag >> 16, (tag >> 8) & 255, tag & 255);
+      if (tag && (v == V_TCPAIR64 || v == V_TCPAIR32)) snprintf(names + 16 * n, 16, "P%dk%dd%d", tag >> 16, (tag >> 8) & 255, tag & 255);
+      else if (tag) snprintf(names + 16 * n, 16, "T%dc%dk%dd%d", v == V_TC128 ? 128 : v == V_TC64 ? 64 : 32, tag >> 16, (tag >> 8) & 255, tag & 255);
       else { strncpy(names + 16 * n, variant_name(v), 15); names[16 * n + 15] = 0; }
     }
     if (ms) ms[n] = m;

@@ -546,6 +546,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcconv_kernel(const TcConvArgs
           mbar_expect_tx(&b_full[it], BYTES);
           tma_bulk_g2s(bring + it * Cfg::SLOT_BYTES, wt + (size_t)it * Cfg::SLOT_BYTES, BYTES, &b_full[it]);
         }
+        // a CTA whose tiles all lie past their utterances never waits on these copies: they must have landed before the
+        // CTA can exit (its shared memory may be handed to the next kernel's CTA)
+        for (int it = 0; it < n_slots; ++it) mbar_wait(&b_full[it], 0u);
       } else {
         int slot = 0;
         uint32_t phase = 1;

@@ -113,6 +113,7 @@ def test_graph_replay_is_bit_identical(native):
     Replays must equal the directly launched sequence bit for bit, follow a new Philox seed, and stop when the
     option is switched off."""
     nat = native.native
+    nat.set_precision("f16x3")       # the default mode: tensor-core kernels, PDL on the WaveNet stacks, concurrent branches
     B, L = 2, 22050
     wav = (torch.rand(B, L, generator=torch.Generator().manual_seed(3)) - 0.5).cuda()
     wlen = torch.tensor([L, L - 3000], dtype=torch.int64, device="cuda")
@@ -149,6 +150,23 @@ def test_graph_replay_is_bit_identical(native):
     seq_g = [call(9) for _ in range(3)][-1]
     nat.set_option("branches", 1)
     assert torch.equal(seq, ref9) and torch.equal(seq_g, ref9)
+
+
+def test_fused_conv_pair_equals_two_launches(native):
+    """OVC_OPT_PAIR: the fused ResBlock conv-pair kernel of the C = 32 stage (intermediate activation kept in shared memory)
+    performs the same arithmetic in the same order as two conv launches: bit-identical audio on a ragged batch whose
+    lengths put tile boundaries, utterance ends and the 118 / 126-step tiling in different places; both tensor-core modes."""
+    spec, lengths, gs, gt, noise = O.synthetic_inputs(3, 131, 17, lengths=[131, 64, 7])
+    outs = {}
+    for mode in ("f16x3", "f16"):
+        native.native.set_precision(mode)
+        for pair in (0, 1):
+            native.native.set_option("pair", pair)
+            o, _, _ = run_native(native, spec, lengths, gs, gt, noise, 0.3, ragged=True)
+            outs[(mode, pair)] = o
+        assert torch.equal(outs[(mode, 0)], outs[(mode, 1)]), mode
+    native.native.set_precision("f16x3")
+    native.native.set_option("pair", 1)
 
 
 def test_flow_roundtrip_property_full_size(native):

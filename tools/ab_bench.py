@@ -45,7 +45,7 @@ def main():
     times = [[] for _ in settings]
 
     def apply(st):
-        for k in ("graph", "pdl", "tune", "wide_variant", "act_tma", "branches"):
+        for k in ("graph", "pdl", "tune", "wide_variant", "act_tma", "branches", "pair"):
             if k in st:
                 nat.set_option(k, st[k])
         if "graph" not in st:

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--wide-variant", type=int, default=None)
     ap.add_argument("--act-tma", type=int, default=None)
     ap.add_argument("--pdl", type=int, default=None)
+    ap.add_argument("--pair", type=int, default=None)
     ap.add_argument("--tune", type=int, default=None)
     ap.add_argument("--reps", type=int, default=1, help="profiled calls (per-variant times are averaged)")
     args = ap.parse_args()
@@ -49,6 +50,8 @@ def main():
         nat.set_option("act_tma", args.act_tma)
     if args.pdl is not None:
         nat.set_option("pdl", args.pdl)
+    if args.pair is not None:
+        nat.set_option("pair", args.pair)
     if args.tune is not None:
         nat.set_option("tune", args.tune)
     nat.set_option("graph", 0)
