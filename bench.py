@@ -532,7 +532,8 @@ def main():
         if not f:
             continue
         key = {"T128": "tcconv_wide_kernel<1> / tcconv_kernel<128> (C >= 128)", "T64c": "tcconv_kernel<64> (C = 64)",
-               "T32c": "tcconv_kernel<32> (C = 32)", "P32k": "tcpair_kernel<32> (C = 32, fused conv pairs; 2 convs per launch)"
+               "T32c": "tcconv_kernel<32> (C = 32)", "P32k": "tcpair_kernel<32> (C = 32, fused k = 3 conv pairs; 2 convs per launch)",
+               "P64k": "tcpair_kernel<64> (C = 64, fused k = 3 conv pairs; 2 convs per launch)"
                }.get(name[:4], "conv1d_f32 (CUDA cores)")
         a = fam.setdefault(key, [0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += ms; a[2] += fl; a[3] += by
@@ -582,8 +583,8 @@ def main():
         tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         traffic, traffic_note = ncu_dram_pass()
         roofline = {
-            "kernel": "tcconv_kernel<128|64|32> + tcconv_wide_kernel<1> (C = 256, k >= 7) + tcpair_kernel<32> (fused k = 3 pairs): "
-                      "the 72 generator ResBlock1 convs on tcgen05, 69 launches per call",
+            "kernel": "tcconv_kernel<128|64|32> + tcconv_wide_kernel<1> (C = 256, k >= 7) + tcpair_kernel<64|32> (fused k = 3 conv pairs): "
+                      f"the 72 generator ResBlock1 convs on tcgen05, {prof['launches'] // max(1, args.steps)} launches per call",
             "bound": "tensor", "achieved": ach_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach_tf / tc_peak,
             "frac_note": "algorithmic FLOPs / time / measured dense 16-bit tensor peak; the fp32-grade split precision needs "
                          "3 MMA passes, so 1/3 is the ceiling of this mode",
