@@ -5,6 +5,9 @@ declare -A WHAT=(
  [s1_k3_c1]="generator stage 1 (C=128, T=55104/clip) ResBlock conv1, k=3"
  [s1_k11_c2]="generator stage 1 (C=128) ResBlock conv2, k=11, with residual"
  [s2_k3_c2]="generator stage 2 (C=64, T=110208/clip) ResBlock conv2, k=3, with residual"
+ [s2_k3_pair]="generator stage 2 (C=64, T=110208/clip) fused ResBlock conv pair, k=3 (tcpair_kernel<64>)"
+ [s3_k3_pair]="generator stage 3 (C=32, T=220416/clip) fused ResBlock conv pair, k=3 (tcpair_kernel<32>)"
+ [s3_k7_c1]="generator stage 3 (C=32) ResBlock conv1, k=7"
  [s2_k11_c1]="generator stage 2 (C=64) ResBlock conv1, k=11"
  [s3_k3_c1]="generator stage 3 (C=32, T=220416/clip) ResBlock conv1, k=3"
  [s3_k3_c2]="generator stage 3 (C=32) ResBlock conv2, k=3, with residual"

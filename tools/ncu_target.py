@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Target process for ncu captures: `calls` convert_waveform calls of batch x secs synthetic clips (default f16x3 mode).
 
-Tensor-core conv launches of ONE call, in order (173): enc WN 32, flow fwd 32, flow rev 32, then the generator:
-conv_pre [96], ups0 [97], stage0 [98..115], ups1 [116], stage1 [117..134], ups2 [135], stage2 [136..153], ups3 [154],
-stage3 [155..172] (within a stage: k=3 | 7 | 11, each c1(d1) c2 c1(d3) c2 c1(d5) c2).  A call launches 214 kernels in all
-(213 + the call-parameter kernel).  See tools/gpu_ncu.sh for the -s / -c arithmetic."""
+Tensor-core conv launches (tcconv_* and tcpair_* kernels) of ONE call, in order (167): enc WN 32, flow fwd 32, flow rev 32,
+then the generator: conv_pre [96], ups0 [97], stage0 [98..115], ups1 [116], stage1 [117..134], ups2 [135], stage2 [136..150],
+ups3 [151], stage3 [152..166].  Within stages 0-1: k=3 | 7 | 11, each c1(d1) c2 c1(d3) c2 c1(d5) c2; within stages 2-3 the three
+k = 3 pairs are ONE fused launch each (d1, d3, d5), then k = 7 and k = 11 as above.  A call launches 208 kernels in all
+(207 + the call-parameter kernel).  See tools/gpu_ncu.sh for the -s / -c arithmetic."""
 import argparse
 import json
 import os
