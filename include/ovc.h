@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OVC_ABI_VERSION 1
+#define OVC_ABI_VERSION 2   /* 2: ovc_graph_replays, OVC_OPT_PDL .. OVC_OPT_PAIR */
 
 #if defined(__GNUC__)
 #define OVC_API __attribute__((visibility("default")))
