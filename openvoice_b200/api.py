@@ -544,7 +544,9 @@ class ToneColorConverter(OpenVoiceBaseClass):
             raise ValueError("audio shorter than the STFT reflect padding")   # torch raises here too
         # host -> device: one pinned staging buffer per slot (cached across calls: cudaHostAlloc is slow), one copy;
         # a slot is restaged only after its previous upload has left it
-        Lmax = max(len(w) for w in waves)
+        # the padded length is rounded up to 16 hops: batches of similar length share one launch signature, so the native
+        # library replays their CUDA graph; every item still runs at its own exact length (ragged), so nothing changes
+        Lmax = -(-max(len(w) for w in waves) // (16 * hop)) * (16 * hop)
         ev = self.__dict__.setdefault("_h2d_done", {}).get(slot)
         if ev is not None:
             ev.synchronize()
@@ -575,7 +577,7 @@ class ToneColorConverter(OpenVoiceBaseClass):
         self._h2d_done[slot] = ev
         nz = None
         if noise is not None:
-            nz = torch.zeros(B, hps.model.inter_channels, Tmax, device=dev, dtype=torch.float32)
+            nz = torch.zeros(B, hps.model.inter_channels, Lmax // hop, device=dev, dtype=torch.float32)
             for b, q in enumerate(noise):
                 q = q.reshape(hps.model.inter_channels, -1)
                 nz[b, :, : q.shape[1]] = q.to(dev)

@@ -152,7 +152,9 @@ def convert_sharded_async(converter, audios: Sequence[np.ndarray], src_se, tgt_s
     samples = [len(a) // hop * hop for a in audios]
     shards = lpt_shard([len(a) for a in audios], world)
     n_max = max(len(sh) for sh in shards)
-    l_max = max(samples) if samples else 0
+    # result blocks are as wide as the longest utterance's launch bucket (convert_batch_device pads to 16 hops), so a rank
+    # whose shard holds it hands its result buffer to the gather without a copy
+    l_max = -(-max(len(a) for a in audios) // (16 * hop)) * (16 * hop) if samples else 0
     mine = shards[rank]
     pick = (lambda se: [se[i] for i in mine]) if isinstance(src_se, (list, tuple)) else (lambda se: se)
     state = converter.__dict__.setdefault("_shard_state", {"n": 0})
@@ -175,7 +177,8 @@ def convert_sharded_async(converter, audios: Sequence[np.ndarray], src_se, tgt_s
         host = _pinned_block(state, f"h{k}", (1, max(n_max, 1), max(l_max, 1)), dev)
         done = None
         if len(mine):
-            host[0, : o.shape[0], : o.shape[1]].copy_(o, non_blocking=True)
+            w = min(o.shape[1], host.shape[2])       # the device result is padded to the launch bucket (16 hops)
+            host[0, : o.shape[0], :w].copy_(o[:, :w], non_blocking=True)
         if dev.type == "cuda":
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(dev))
@@ -192,7 +195,8 @@ def convert_sharded_async(converter, audios: Sequence[np.ndarray], src_se, tgt_s
     block = o
     if o.shape[0] != n_max or o.shape[1] != l_max:
         block = torch.zeros(n_max, max(l_max, 1), dtype=torch.float32, device=dev)
-        block[: o.shape[0], : o.shape[1]] = o
+        w = min(o.shape[1], l_max)                   # the device result is padded to the launch bucket (16 hops)
+        block[: o.shape[0], :w] = o[:, :w]
         if cuda:
             ready.record(torch.cuda.current_stream(dev))
     host = None
