@@ -305,3 +305,92 @@ def test_on_device_watermark_chunking_matches_the_reference_loop(capsys):
 def test_streaming_module_imports_without_gpu():
     import openvoice_b200.streaming as S
     assert hasattr(S, "StreamingConverter")
+
+
+def test_streaming_state_machine_with_a_stand_in_converter():
+    """Host logic of StreamingConverter on the CPU: spectrogram frames computed from audio segments (a frame is taken only
+    when its STFT support is complete; reflect padding only at the true ends of the stream), noise / frame bookkeeping,
+    window + halo scheduling, flush -- with the oracle's STFT and a stand-in 'voice conversion' whose output at frame t
+    depends on frames t-100 .. t+100 and on that frame's noise, so a wrong frame, offset or halo shows up."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from oracle import vc_oracle as O
+    from openvoice_b200.streaming import StreamingConverter
+
+    kern = torch.linspace(0.2, 1.0, 201)[None, None]
+
+    class FakeNative:
+        def spectrogram(self, wav, wlen):
+            T = wav.shape[1] // 256
+            return O.spectrogram(wav)[:, :, :T], torch.tensor([T])
+
+    class FakeModel:
+        native = FakeNative()
+
+        def voice_conversion(self, sp, lens, src, tgt, tau=0.3, noise=None, ragged=True, latents=False):
+            f = sp[:, :8].mean(1, keepdim=True) + tau * noise[:, :1]           # [1, 1, T]
+            g = F.conv1d(f, kern, padding=100)                                  # receptive field +-100 frames, zero padding
+            o = (g.transpose(1, 2) * torch.linspace(1.0, 2.0, 256)[None, None]).reshape(1, 1, -1)
+            return o, None, None
+
+    class FakeConverter:
+        class hps:
+            class data:
+                hop_length, filter_length = 256, 1024
+
+            class model:
+                inter_channels = 4
+        HALO_FRAMES = 128
+        device = "cpu"
+        model = FakeModel()
+
+        def _stack_se(self, se, n):
+            return se.reshape(1, -1)
+
+    rng = np.random.default_rng(5)
+    L = 22050 * 7 + 131
+    wav = rng.standard_normal(L).astype(np.float32)
+    T = L // 256
+    noise = torch.randn(4, T, generator=torch.Generator().manual_seed(2))
+    se = torch.zeros(1, 8, 1)
+    conv = FakeConverter()
+    sp, _ = conv.model.native.spectrogram(torch.from_numpy(wav)[None], None)
+    whole = conv.model.voice_conversion(sp, None, None, None, tau=0.3, noise=noise[None])[0][0, 0].numpy()
+    for W, sizes in ((64, [1000, 37, 50000, 256, 8191]), (300, [22050]), (1, [4096])):
+        sc = StreamingConverter(conv, se, se, tau=0.3, window_frames=W, noise_fn=lambda a, b: noise[:, a:b])
+        outs, pos, i, peak = [], 0, 0, 0
+        while pos < L:
+            n = min(sizes[i % len(sizes)], L - pos)
+            outs.append(sc.push(wav[pos: pos + n]))
+            pos += n
+            i += 1
+            peak = max(peak, sc.state_frames)
+            assert sum(len(o) for o in outs) % 256 == 0 and sum(len(o) for o in outs) // 256 <= max(0, (pos - 640) // 256 + 1)
+        outs.append(sc.flush())
+        got = np.concatenate(outs)
+        assert got.shape == whole.shape == (256 * T,)
+        assert np.allclose(got, whole, rtol=1e-5, atol=1e-5), (W, float(np.abs(got - whole).max()))
+        assert peak <= W + 2 * 128 + max(sizes) // 256 + 8
+    # a stream that ends before the first window is complete: everything comes out of flush
+    sc = StreamingConverter(conv, se, se, tau=0.3, window_frames=200, noise_fn=lambda a, b: noise[:, a:b])
+    assert len(sc.push(wav[:30000])) == 0
+    tail = sc.flush()
+    sp2, _ = conv.model.native.spectrogram(torch.from_numpy(wav[:30000])[None], None)
+    ref2 = conv.model.voice_conversion(sp2, None, None, None, tau=0.3, noise=noise[None, :, : 30000 // 256])[0][0, 0].numpy()
+    assert tail.shape == ref2.shape and np.allclose(tail, ref2, rtol=1e-5, atol=1e-5)
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native arm): one JSON line with the native arm's
+    metric / unit / config and the e2e / cpu_baseline objects the tier contract asks for."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-clips", "1", "--secs", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "audio_seconds_per_second" and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["config"]["batch_per_gpu"] == 32 and "workload" in line["config"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
