@@ -13,11 +13,11 @@ broadcasts the checkpoint and, in the end-to-end leg, gathers the output wavefor
 
 One JSON line on stdout (rank 0):
   value      device-resident: waveforms already in HBM -> ovc_convert_waveform (STFT + voice_conversion), CUDA events
-  e2e        HOST numpy waveforms in, HOST numpy waveforms out, all inside the timed region: N = 1 through
-             ToneColorConverter.convert_batch (pinned H2D, kernels, D2H); N > 1 through
-             openvoice_b200.distributed.convert_sharded_async (each rank uploads and converts its shard, the
-             results are gathered GPU-to-GPU over NCCL and downloaded on rank 0; one call in flight behind the
-             current one, so a step's gather + download overlap the next step's kernels)
+  e2e        HOST numpy waveforms in, HOST numpy waveforms out, all inside the timed region, through
+             openvoice_b200.distributed.convert_sharded_async at every N (each rank stages, uploads from pinned memory
+             and converts its shard; N > 1: results gathered GPU-to-GPU over NCCL; rank 0 downloads; one call in flight
+             behind the current one, so a step's download overlaps the next step's kernels).  At N = 1 the synchronous
+             ToneColorConverter.convert_batch is timed beside it (`e2e_convert_batch`)
   roofline   generator ResBlock conv family (90 % of the FLOPs), timed live with CUDA events around every launch:
              ALGORITHMIC TFLOP/s (2*MAC of the reference's convs, no credit for the 3 split-precision passes) over
              the measured dense fp16/bf16 tensor peak; pipe occupancy, HBM figures and a per-kernel table beside it
@@ -438,36 +438,31 @@ def main():
             modes[mode] = world * audio_s_step / (max_over_ranks(m0.elapsed_time(m1)) / 2 * 1e-3)
         native.set_precision(args.precision)
 
-    # ---- end-to-end leg: host numpy in, host numpy out, through the public API
-    if world == 1:
-        def e2e_run(n):
-            res = None
-            for _ in range(n):
-                res = conv.convert_batch(waves, src, tgt, tau=0.3, max_batch=B)
-            return res
-        h2d, d2h = int(B * L * 4 + B * 8), int(B * T * HOP * 4)
-        e2e_api = "ToneColorConverter.convert_batch"
-    else:
-        # every rank holds the global utterance list (world * B clips); LPT sharding gives each rank B of them
-        all_waves = [synth_wave(i, secs) for i in range(world * B)]
-        all_src = [synth_se(i, 2000) for i in range(world * B)]
-        all_tgt = [synth_se(i, 3000) for i in range(world * B)]
+    # ---- end-to-end leg: host numpy in, host numpy out, through the public API.  The same pipelined call at every N:
+    # openvoice_b200.distributed.convert_sharded_async -- each rank stages + uploads + converts its shard, the results are
+    # gathered GPU-to-GPU (N > 1) and downloaded on rank 0, ONE call in flight behind the current one, so step i's
+    # download overlaps step i+1's kernels; every step's inputs cross PCIe from pinned memory and every step's results
+    # land in host memory inside the timed region.  (The synchronous ToneColorConverter.convert_batch is timed beside
+    # it at N = 1 as `e2e_convert_batch`.)
+    all_waves = waves if world == 1 else [synth_wave(i, secs) for i in range(world * B)]
+    all_src = [synth_se(i, 2000) for i in range(world * B)]
+    all_tgt = [synth_se(i, 3000) for i in range(world * B)]
 
-        def e2e_run(n):
-            res, prev = None, None
-            for _ in range(n):
-                job = D.convert_sharded_async(conv, all_waves, all_src, all_tgt, tau=0.3)
-                if prev is not None:
-                    res = prev.result()      # step i's waveforms are on the host while step i+1 computes
-                prev = job
-            res = prev.result()
-            return res
-        h2d, d2h = int(B * L * 4 + B * 8), int(world * B * T * HOP * 4)
-        e2e_api = "openvoice_b200.distributed.convert_sharded_async (one call in flight; d2h on rank 0 only)"
+    def e2e_run(n):
+        res, prev = None, None
+        for _ in range(n):
+            job = D.convert_sharded_async(conv, all_waves, all_src, all_tgt, tau=0.3)
+            if prev is not None:
+                res = prev.result()      # step i's waveforms are on the host while step i+1 computes
+            prev = job
+        res = prev.result()
+        return res
+    h2d, d2h = int(B * L * 4 + B * 8), int(world * B * T * HOP * 4)
+    e2e_api = "openvoice_b200.distributed.convert_sharded_async (one call in flight; d2h on rank 0 only)"
 
     # untimed: W steps, and at least enough for both upload slots of the sharded path to have captured their CUDA graph
     # (a launch signature is captured the second time it is seen; a capture + instantiation costs ~10 ms once)
-    e2e_run(args.warmup if world == 1 else max(args.warmup, 6))
+    e2e_run(max(args.warmup, 6))
     barrier()
     t0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -480,6 +475,17 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         assert len(res) == world * B and res[0].shape[0] == T * HOP and np.isfinite(res[0]).all() and np.isfinite(res[-1]).all()
+    e2e_sync = None
+    if world == 1:
+        for _ in range(3):
+            conv.convert_batch(waves, src, tgt, tau=0.3, max_batch=B)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(max(2, args.steps // 2)):
+            conv.convert_batch(waves, src, tgt, tau=0.3, max_batch=B)
+        ms_sync = (time.perf_counter() - t1) * 1e3 / max(2, args.steps // 2)
+        e2e_sync = {"value": audio_s_step / (ms_sync * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_sync,
+                    "what": "ToneColorConverter.convert_batch (synchronous: stage, upload, convert, download, unpack per call)"}
 
     # ---- config 4 (V2 converter: zero_g, 16 clips of 10 s per GPU, sharded): side key
     config4 = None
@@ -618,6 +624,8 @@ def main():
         "launches_per_call": int(launches_per_call),
         "roofline": roofline, "clocks": clocks,
     }
+    if e2e_sync is not None:
+        line["e2e_convert_batch"] = e2e_sync
     if config4 is not None:
         line["config4"] = config4
     if world == 1 and not args.no_sides:

@@ -176,13 +176,23 @@ def convert_sharded_async(converter, audios: Sequence[np.ndarray], src_se, tgt_s
     if world == 1:
         host = _pinned_block(state, f"h{k}", (1, max(n_max, 1), max(l_max, 1)), dev)
         done = None
-        if len(mine):
-            w = min(o.shape[1], host.shape[2])       # the device result is padded to the launch bucket (16 hops)
-            host[0, : o.shape[0], :w].copy_(o[:, :w], non_blocking=True)
+        w = min(o.shape[1], host.shape[2])           # the device result is padded to the launch bucket (16 hops)
         if dev.type == "cuda":
-            done = torch.cuda.Event()
-            done.record(torch.cuda.current_stream(dev))
+            # download on a side stream: the next call's upload and kernels do not queue behind it
+            side = state.get("side")
+            if side is None:
+                side = state["side"] = torch.cuda.Stream(dev)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                if len(mine):
+                    host[0, : o.shape[0], :w].copy_(o[:, :w], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(side)
             state[f"done{k}"] = done
+        elif len(mine):
+            host[0, : o.shape[0], :w].copy_(o[:, :w])
         return ShardedJob(done, table, host.numpy(), rank, dst, len(audios), copy)
     # fixed-shape block per rank (pad rows / columns), gathered on a side stream
     cuda = dev.type == "cuda"

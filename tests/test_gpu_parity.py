@@ -440,6 +440,36 @@ def test_streaming_equals_whole_clip(tmp_path, synthetic_sd):
     assert tail.shape == short.shape and rel_err(tail, short) <= 2e-6
 
 
+def test_pipelined_single_gpu_api_equals_convert(tmp_path, synthetic_sd):
+    """openvoice_b200.distributed.convert_sharded_async on one GPU (what bench.py's end-to-end leg calls): three calls
+    back to back with one in flight -- upload slots alternate, downloads run on a side stream, graphs are captured and
+    replayed -- return, per utterance, exactly what ToneColorConverter.convert returns (tau = 0: no random draw)."""
+    from openvoice_b200 import distributed as D
+    from openvoice_b200.api import ToneColorConverter
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps(O.DEFAULT_HPARAMS))
+    conv = ToneColorConverter(str(cfg), device="cuda:0", enable_watermark=False)
+    conv.model.load_state_dict(synthetic_sd)
+    rng = np.random.default_rng(31)
+    waves = [(0.5 * (2 * rng.random(n, dtype=np.float32) - 1)).astype(np.float32) for n in (22050, 9000, 30011, 4096)]
+    gen = torch.Generator().manual_seed(3)
+    src = [0.1 * torch.randn(1, 256, 1, generator=gen) for _ in waves]
+    tgt = [0.1 * torch.randn(1, 256, 1, generator=gen) for _ in waves]
+    solo = [conv.convert(w, s, t, tau=0.0) for w, s, t in zip(waves, src, tgt)]
+    jobs = []
+    for _ in range(5):
+        jobs.append(D.convert_sharded_async(conv, waves, src, tgt, tau=0.0, copy=True))
+        if len(jobs) >= 2:
+            res = jobs[-2].result()
+            assert len(res) == len(waves)
+            for a, b in zip(res, solo):
+                assert a.shape == b.shape and np.array_equal(a, b)
+    last = jobs[-1].result()
+    for a, b in zip(last, solo):
+        assert np.array_equal(a, b)
+    assert conv.model.native.graph_replays > 0
+
+
 def test_api_convert_matches_reference_golden(tmp_path, synthetic_sd):
     """ToneColorConverter.convert end to end (waveform -> spectrogram -> VC -> samples) against
     the real reference's convert() output."""
