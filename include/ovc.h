@@ -194,11 +194,12 @@ OVC_API int ovc_set_precision(ovc_ctx* ctx, int mode);
 #define OVC_OPT_GRAPH 3
 #define OVC_OPT_ACT_TMA 4
 #define OVC_OPT_PDL 5
-#define OVC_OPT_BRANCHES 7   /* 1 (default): latency-bound calls (B * Tmax <= 512 frames) run the three ResBlock branches of an MRF stage
-                              * concurrently (three streams, a third of the SMs per kernel); results are bit-identical */
-#define OVC_OPT_PAIR 8       /* 1 (default): the HBM-bound ResBlock conv pairs (C = 32, k <= 5) run as ONE kernel each
+#define OVC_OPT_TUNE 6       /* A/B bits of the persistent conv kernel: 1 = L2 prefetch of the residual tile (default off),
+                              * 2 = two items per converter iteration (default on) */
+#define OVC_OPT_BRANCHES 7   /* 1 (default): latency-bound calls (B * Tmax <= 512 frames) run the three ResBlock branches of an
+                              * MRF stage concurrently (three streams, a third of the SMs per kernel); results are bit-identical */
+#define OVC_OPT_PAIR 8       /* 1 (default): the HBM-bound ResBlock conv pairs (C <= 64, k = 3) run as ONE kernel each
                               * (ovc_tcpair.cuh): the intermediate activation stays in shared memory; same bits as two launches */
-#define OVC_OPT_TUNE 6   /* A/B bits of the persistent conv kernel: 1 = L2 prefetch of the residual tile, 2 = two items per converter iteration */
 OVC_API int ovc_set_option(ovc_ctx* ctx, int key, int value);
 
 /* Number of kernels the last ovc_voice_conversion / ovc_convert_waveform call launched. */
